@@ -1,0 +1,194 @@
+/*
+ * tapstark.h -- C ABI of libtapstark_b200.so: the B200-native (sm_100a) prover commitment hot path of
+ * TapSTARK (bitlayer-org/tap-stark).
+ *
+ * The reference is a Rust workspace with no FFI boundary; the replaceable units are three Plonky3-derived
+ * traits.  Each entry point below names the reference interface it stands in for (paths relative to the
+ * reference checkout).  A Rust shim (tap-stark_b200/rust/) implements those traits by
+ * calling this ABI; statuses != TS_OK are turned into panics there, matching the reference's
+ * assert!/expect convention.
+ *
+ * Conventions
+ *   - BabyBear elements are u32 in MONTGOMERY form (x * 2^32 mod p, p = 0x78000001): the in-memory form of
+ *     p3-baby-bear's `BabyBear` at Plonky3 rev 72b2fc16 [MEM], so a Rust Vec<BabyBear> is passed as-is.
+ *   - BabyBear^4 (BinomialExtensionField<BabyBear,4>, basic/src/field/mod.rs:53-64) = 4 consecutive u32,
+ *     low-degree coefficient first.  An extension matrix h x w is a base matrix h x 4w.
+ *   - Matrices are row-major (p3-matrix RowMajorMatrix), rows = height, width in u32 elements.
+ *   - "committed order" = rows bit-reversed, i.e. what
+ *     `dft.coset_lde_batch(..).bit_reverse_rows().to_row_major_matrix()` yields
+ *     (fri/src/two_adic_pcs.rs:237-240).
+ *   - Digests / commitments are 32 bytes = [[u8;4];8] as observed by the challenger
+ *     (basic/src/challenger/mod.rs:197-223).
+ *   - A ts_ctx is used by one host thread at a time.  All work is enqueued on the ctx stream; entry points
+ *     that return host-visible results synchronise that stream before returning.
+ *   - No CPU fallback exists: without a CUDA device ts_ctx_create fails.
+ */
+#ifndef TAPSTARK_H
+#define TAPSTARK_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TS_OK 0
+#define TS_ERR_CUDA 1
+#define TS_ERR_ARG 2
+#define TS_ERR_NOT_CONSTANT 3 /* fri/src/prover.rs:130-134 final layer not constant */
+#define TS_ERR_NO_WITNESS 4   /* basic/src/challenger/mod.rs:101 "failed to find witness" */
+
+#define TS_P 0x78000001u
+#define TS_GENERATOR_MONTY 0x0fffffbeu /* 31 in Montgomery form: Val::generator(), two_adic_pcs.rs:235 */
+
+typedef struct ts_ctx ts_ctx;
+typedef struct ts_matrix ts_matrix; /* device-resident RowMajorMatrix<BabyBear> */
+typedef struct ts_tree ts_tree;     /* BFMmcs::ProverData: digest layers + the committed matrices */
+typedef struct ts_challenger ts_challenger;
+
+/* ---------------------------------------------------------------- context */
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a private stream. */
+int ts_ctx_create(int device, void *stream, ts_ctx **out);
+void ts_ctx_destroy(ts_ctx *ctx);
+const char *ts_last_error(const ts_ctx *ctx);
+int ts_ctx_synchronize(ts_ctx *ctx);
+/* 1 if this library was built for a real GPU (always, for the shipped library). */
+int ts_is_device_build(void);
+
+/* Per-kernel-class device timers (CUDA events on the ctx stream), for bench.py's roofline.
+ * kind: see TS_K_*.  Returns accumulated ms and launch count since the last reset. */
+#define TS_K_NTT_PASS 0  /* in-place DIF digit pass (ntt.cuh: ntt_pass_kernel) */
+#define TS_K_LDE_MID 1   /* fused inverse-last-digit + coset scale + forward-first-digit (lde_mid_kernel) */
+#define TS_K_HASH_LEAVES 2
+#define TS_K_TREE 3
+#define TS_K_FOLD 4
+#define TS_K_MISC 5
+#define TS_K_COUNT 6
+int ts_ctx_set_profiling(ts_ctx *ctx, int on);
+int ts_ctx_reset_stats(ts_ctx *ctx);
+int ts_ctx_get_stats(ts_ctx *ctx, int kind, double *ms, uint64_t *launches);
+uint64_t ts_ctx_total_launches(const ts_ctx *ctx);
+
+/* ---------------------------------------------------------------- matrices */
+int ts_matrix_alloc(ts_ctx *ctx, size_t rows, size_t width, ts_matrix **out);
+/* copies a host RowMajorMatrix (Montgomery u32) to the device (pinned staging is the caller's business) */
+int ts_matrix_from_host(ts_ctx *ctx, const uint32_t *host, size_t rows, size_t width, ts_matrix **out);
+/* copies from a device pointer (device-to-device) */
+int ts_matrix_from_device(ts_ctx *ctx, const uint32_t *dev, size_t rows, size_t width, ts_matrix **out);
+/* wraps caller-owned device memory without copying; the caller keeps it alive */
+int ts_matrix_wrap_device(ts_ctx *ctx, uint32_t *dev, size_t rows, size_t width, ts_matrix **out);
+/* rows [row0, row0+nrows) -> host.  Serves BFMmcs::get_matrices (basic/src/mmcs/bf_mmcs.rs:52) and
+ * Pcs::get_evaluations_on_domain (fri/src/two_adic_pcs.rs:247-258). */
+int ts_matrix_download(ts_ctx *ctx, const ts_matrix *m, size_t row0, size_t nrows, uint32_t *host);
+uint32_t *ts_matrix_device_ptr(const ts_matrix *m);
+size_t ts_matrix_rows(const ts_matrix *m);
+size_t ts_matrix_width(const ts_matrix *m);
+void ts_matrix_free(ts_matrix *m);
+/* in-place canonical <-> Montgomery on the device (helpers for hosts that hold canonical values) */
+int ts_matrix_to_monty(ts_ctx *ctx, ts_matrix *m);
+int ts_matrix_from_monty(ts_ctx *ctx, ts_matrix *m);
+/* out = bit-reversed-rows copy of m (p3-matrix bit_reverse_rows().to_row_major_matrix()) */
+int ts_matrix_bit_reverse_rows(ts_ctx *ctx, const ts_matrix *m, ts_matrix **out);
+
+/* ---------------------------------------------------------------- p3_dft::TwoAdicSubgroupDft<BabyBear>
+ * Replaces the `Dft` parameter of TwoAdicFriPcs (fri/src/two_adic_pcs.rs:207, used at :237-240).
+ * `evals`/`coeffs` are consumed logically (the trait takes the matrix by value) but NOT freed or modified.
+ * Outputs are new device matrices owned by the caller.
+ *   ts_coset_lde_batch : the PCS hot call.  out = coset_lde_batch(evals, added_bits, shift) in COMMITTED
+ *                        (bit-reversed) row order, (rows<<added_bits) x width.
+ *   natural_order != 0 : undo the bit reversal (plain trait semantics, one extra permutation pass).      */
+int ts_coset_lde_batch(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
+                       int natural_order, ts_matrix **out);
+int ts_dft_batch(ts_ctx *ctx, const ts_matrix *coeffs, ts_matrix **out);                       /* natural -> natural */
+int ts_idft_batch(ts_ctx *ctx, const ts_matrix *evals, ts_matrix **out);                       /* natural -> natural */
+int ts_coset_dft_batch(ts_ctx *ctx, const ts_matrix *coeffs, uint32_t shift_monty, ts_matrix **out);
+int ts_lde_batch(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, ts_matrix **out);   /* shift = 1, natural */
+/* Host-buffer form of the hot call (what a drop-in `impl TwoAdicSubgroupDft for GpuDft` does):
+ * H2D, LDE, D2H.  out_host must hold (rows<<added_bits)*width u32; committed order unless natural_order. */
+int ts_coset_lde_batch_host(ts_ctx *ctx, const uint32_t *evals_host, size_t rows, size_t width,
+                            unsigned added_bits, uint32_t shift_monty, int natural_order, uint32_t *out_host);
+
+/* ---------------------------------------------------------------- basic::mmcs::bf_mmcs::BFMmcs<T>
+ * (basic/src/mmcs/bf_mmcs.rs:17-68).  Blake3 row hash + 2-to-1 Blake3 tree over device-resident matrices.
+ *   TS_LAYOUT_P3_INJECT : [MEM] p3-merkle-tree FieldMerkleTreeMmcs<.., SerializingHasher32<Blake3>,
+ *                         CompressionFunctionFromHasher<u8,Blake3,2,32>, 32> (north_star's "Blake3 Merkle").
+ *   TS_LAYOUT_PADDED    : one leaf layer whose leaf i concatenates, largest matrix first, row
+ *                         i >> (log_max - log_h) of every matrix -- the reference's padding_matrix
+ *                         (basic/src/tcs/mod.rs:339-378).
+ * Heights must be powers of two.  Matrices are BORROWED unless take_ownership != 0 (then the tree frees them). */
+#define TS_LAYOUT_P3_INJECT 0
+#define TS_LAYOUT_PADDED 1
+int ts_mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, int take_ownership,
+                   uint8_t root[32], ts_tree **out);
+size_t ts_tree_num_matrices(const ts_tree *t);
+ts_matrix *ts_tree_matrix(const ts_tree *t, size_t i); /* BFMmcs::get_matrices */
+size_t ts_tree_depth(const ts_tree *t);                /* siblings in an opening */
+size_t ts_tree_max_height(const ts_tree *t);           /* BFMmcs::get_max_height */
+/* BFMmcs::open_batch(query_index): rows_out receives every matrix's opened row (Montgomery) concatenated
+ * in caller order (sum of widths u32); path_out receives depth x 32 bytes. */
+int ts_mmcs_open_batch(ts_ctx *ctx, const ts_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out);
+/* BFMmcs::verify_batch; host-side (the verifier is out of scope for the GPU). returns TS_OK / TS_ERR_ARG */
+int ts_mmcs_verify_batch(const size_t *heights, const size_t *widths, size_t n_mats, int layout, size_t index,
+                         const uint32_t *rows_monty, const uint8_t *path, size_t depth, const uint8_t root[32]);
+/* copies digest layer `layer` (0 = leaves) to host, 32 bytes per node */
+int ts_tree_layer(ts_ctx *ctx, const ts_tree *t, size_t layer, uint8_t *out, size_t *n_nodes);
+void ts_tree_free(ts_tree *t);
+
+/* ---------------------------------------------------------------- BfChallenger<F, U32, Blake3Permutation, 16>
+ * (basic/src/challenger/mod.rs, chan_field.rs).  Host-side state, 64-byte sponge.  Sampled field values
+ * are returned CANONICAL (they are transcript integers), ext = 4 coefficients. */
+int ts_challenger_new(ts_challenger **out);
+int ts_challenger_clone(const ts_challenger *c, ts_challenger **out);
+void ts_challenger_free(ts_challenger *c);
+void ts_challenger_observe(ts_challenger *c, const uint8_t word[4]);
+void ts_challenger_observe_digest(ts_challenger *c, const uint8_t digest[32]);
+uint32_t ts_challenger_sample_base(ts_challenger *c);
+void ts_challenger_sample_ext(ts_challenger *c, uint32_t out[4]);
+size_t ts_challenger_sample_bits(ts_challenger *c, unsigned bits, int ext);
+int ts_challenger_check_witness(ts_challenger *c, unsigned bits, uint32_t witness, int ext);
+/* deterministic: the smallest valid witness in 0..4096 (the reference's rayon find_any is racy) */
+int ts_challenger_grind(ts_challenger *c, unsigned bits, int ext, uint32_t *witness);
+
+/* ---------------------------------------------------------------- FRI fold
+ * TwoAdicFriGenericConfig::fold_matrix (fri/src/two_adic_pcs.rs:116-147) == fold_even_odd
+ * (fri/src/fold_even_odd.rs:20-52).  in: 2h elements viewed as h x 2; out: h elements.
+ * beta is Montgomery form (1 u32 for base, 4 for ext).  Pointers are DEVICE pointers. */
+int ts_fri_fold_base(ts_ctx *ctx, const uint32_t *in_dev, size_t h, uint32_t beta_monty, uint32_t *out_dev);
+int ts_fri_fold_ext(ts_ctx *ctx, const uint32_t *in_dev, size_t h, const uint32_t beta_monty[4],
+                    uint32_t *out_dev);
+/* host-buffer form (what the fri crate's fold_even_odd(Vec<F>, beta) -> Vec<F> binds to) */
+int ts_fri_fold_ext_host(ts_ctx *ctx, const uint32_t *in_host, size_t h, const uint32_t beta_monty[4],
+                         uint32_t *out_host);
+
+/* ---------------------------------------------------------------- FRI commit phase
+ * bf_commit_phase (fri/src/prover.rs:93-141): commit layer -> observe -> sample beta -> fold -> add the
+ * next input of equal length, until `blowup` values remain; they must all be equal.
+ * inputs: device matrices of EF elements (width 4, one row per element), lengths strictly descending
+ * (two_adic_pcs.rs:389).  Outputs: commits (rounds x 32 bytes), trees[round] (prover data for the query
+ * phase, each owning its layer -- round 0 holds a clone of inputs[0] like the reference's folded.clone();
+ * pass NULL to discard and skip the clone), final_poly (canonical, 4 u32), *rounds. */
+int ts_fri_commit_phase(ts_ctx *ctx, ts_matrix *const *inputs, size_t n_inputs, unsigned log_blowup,
+                        ts_challenger *chal, uint8_t *commits, ts_tree **trees, uint32_t final_poly[4],
+                        size_t *rounds);
+
+/* ---------------------------------------------------------------- Pcs (basic/src/bf_pcs.rs:19-88)
+ * TwoAdicFriPcs::commit (fri/src/two_adic_pcs.rs:227-245): for every (domain, evals):
+ * shift = generator / domain.shift; LDE; bit-reverse rows; one MMCS commit over all LDEs.
+ * domain_shifts_monty[i] is domain.shift (Montgomery); evals borrowed; the tree owns the LDE matrices. */
+int ts_pcs_commit(ts_ctx *ctx, ts_matrix *const *evals, const uint32_t *domain_shifts_monty, size_t n,
+                  unsigned log_blowup, int layout, uint8_t root[32], ts_tree **out);
+/* host-buffer form: evals_host[i] is rows[i] x widths[i] */
+int ts_pcs_commit_host(ts_ctx *ctx, const uint32_t *const *evals_host, const size_t *rows, const size_t *widths,
+                       const uint32_t *domain_shifts_monty, size_t n, unsigned log_blowup, int layout,
+                       uint8_t root[32], ts_tree **out);
+/* Pcs::get_evaluations_on_domain (two_adic_pcs.rs:247-258): first `domain_size` committed rows of matrix
+ * idx, re-bit-reversed -> host (domain.shift must be the generator). */
+int ts_pcs_get_evaluations_on_domain(ts_ctx *ctx, const ts_tree *t, size_t idx, size_t domain_size,
+                                     uint32_t *out_host);
+/* sum_i alpha^i * column_i of a committed matrix -> EF vector (rows x 4): the hot inner loop of
+ * TwoAdicFriPcs::open (`mat.dot_ext_powers(alpha)`, two_adic_pcs.rs:375).  alpha Montgomery. */
+int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,140 @@
+// fold.cuh -- FRI commit-phase even/odd fold and the reduced-opening column combination (sm_100a).
+//
+// fold: TwoAdicFriGenericConfig::fold_matrix (fri/src/two_adic_pcs.rs:116-147) == fold_even_odd
+// (fri/src/fold_even_odd.rs:20-52):
+//     out[i] = (1/2 + pw_i) * lo + (1/2 - pw_i) * hi,   pw_i = (beta/2) * g_inv^bitrev(i),
+//     g_inv = two_adic_generator(log h + 1)^-1, (lo, hi) = row i of the h x 2 view.
+// Computed as out[i] = (lo+hi)/2 + (beta/2) * [ g_inv^bitrev(i) * (lo-hi) ]  (same field element, exact).
+// The reference materialises and bit-reverse-permutes the `powers` vector every call; here
+// g_inv^bitrev(i) = T_lo[i mod 256] * T_hi(i div 256): T_lo is a 256-entry size-independent table
+// (w_512^-bitrev8(t)), T_hi one scalar per CTA chunk, so the kernel streams 32 B in / 16 B out per element
+// with no other global traffic.
+#pragma once
+#include "field.cuh"
+
+namespace fold {
+
+constexpr int FOLD_T = 256;
+
+TS_D uint32_t brev_bits(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+struct InvRootPows {
+    uint32_t v[28];  // v[k] = (w_{2h}^-1)^(2^k), Montgomery
+};
+TS_D uint32_t pow_from_table(const InvRootPows &rp, uint32_t e) {
+    uint32_t acc = bb::MONTY_ONE;
+    for (int k = 0; e; k++, e >>= 1)
+        if (e & 1) acc = bb::mmul(acc, rp.v[k]);
+    return acc;
+}
+
+// delta table: D.v[t] = g_inv^(bitrev(c+1) - bitrev(c)) for a chunk index c with t trailing one bits, so a
+// CTA walking consecutive 256-element chunks updates its per-chunk scalar with ONE multiply.
+struct ChunkDeltas {
+    uint32_t v[28];
+};
+
+// EF fold.  in: 2h EF (8 u32 per output row), out: h EF.  addend (optional): the next FRI input of length h
+// (fri/src/prover.rs:124-126), added after folding.  tlo[t] = (w_512^-1)^bitrev8(t) (Montgomery), used when
+// log_h >= 8; smaller layers take the direct power.
+__global__ void __launch_bounds__(FOLD_T) fold_ext_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                          const uint4 *__restrict__ addend, int log_h,
+                                                          ef::E4 half_beta, InvRootPows rp, ChunkDeltas dl,
+                                                          const uint32_t *__restrict__ tlo) {
+    const ef::E4Const hb = ef::prepare(half_beta);
+    const size_t h = (size_t)1 << log_h;
+    size_t c0 = 0, c1 = 1;
+    uint32_t t_lo = bb::MONTY_ONE, t_hi = bb::MONTY_ONE;
+    const bool chunked = log_h >= 8;
+    if (chunked) {
+        const size_t chunks = h >> 8, cpb = (chunks + gridDim.x - 1) / gridDim.x;
+        c0 = (size_t)blockIdx.x * cpb;
+        c1 = c0 + cpb < chunks ? c0 + cpb : chunks;
+        if (c0 >= c1) return;
+        t_lo = tlo[threadIdx.x];
+        t_hi = pow_from_table(rp, brev_bits((uint32_t)c0, log_h - 8));
+    } else if (blockIdx.x > 0) {
+        return;
+    }
+    for (size_t c = c0; c < c1; c++) {
+        const size_t i = (c << 8) + threadIdx.x;
+        if (i < h) {
+            const uint32_t s = chunked ? bb::mmul(t_lo, t_hi) : pow_from_table(rp, brev_bits((uint32_t)i, log_h));
+            const uint4 a = in[2 * i], b = in[2 * i + 1];
+            ef::E4 lo{{a.x, a.y, a.z, a.w}}, hi{{b.x, b.y, b.z, b.w}};
+            const ef::E4 sum = ef::half(ef::add(lo, hi));
+            const ef::E4 dif = ef::scale(ef::sub(lo, hi), s);
+            ef::E4 r = ef::add(sum, ef::mul(dif, hb));
+            if (addend) {
+                const uint4 x = addend[i];
+                r = ef::add(r, ef::E4{{x.x, x.y, x.z, x.w}});
+            }
+            out[i] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
+        }
+        // trailing ones of c -> which delta moves bitrev(c) to bitrev(c+1)
+        int t = 0;
+        for (size_t cc = c; cc & 1; cc >>= 1) t++;
+        t_hi = bb::mmul(t_hi, dl.v[t < 27 ? t : 27]);
+    }
+}
+
+// Base-field fold (the reference's own fold test and fri/tests/fri.rs run FRI over BabyBear itself).
+__global__ void __launch_bounds__(FOLD_T) fold_base_kernel(const uint2 *__restrict__ in, uint32_t *__restrict__ out,
+                                                           int log_h, uint32_t half_beta, InvRootPows rp) {
+    const size_t h = (size_t)1 << log_h;
+    for (size_t i = (size_t)blockIdx.x * FOLD_T + threadIdx.x; i < h; i += (size_t)gridDim.x * FOLD_T) {
+        const uint32_t s = pow_from_table(rp, brev_bits((uint32_t)i, log_h));
+        const uint2 v = in[i];
+        const uint32_t sum = bb::half(bb::add(v.x, v.y));
+        const uint32_t dif = bb::mmul(bb::sub(v.x, v.y), s);
+        out[i] = bb::add(sum, bb::mmul(dif, half_beta));
+    }
+}
+
+// dot_ext_powers: out[r] = sum_c alpha^c * m[r][c]  (fri/src/two_adic_pcs.rs:375, `mat.dot_ext_powers(alpha)`).
+// alpha powers (Montgomery EF) come precomputed in `apow` (width entries).  One thread per row segment:
+// a CTA stages rows coalesced through shared memory, then thread t reduces row t.
+constexpr int DOT_ROWS = 64;
+constexpr int DOT_COLS = 64;
+__global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__restrict__ m, size_t rows, uint32_t width,
+                                                             const uint4 *__restrict__ apow, uint4 *__restrict__ out) {
+    TS_DYN_SMEM(uint32_t, sm);  // DOT_ROWS x (DOT_COLS+1) data, then 4 partial sets
+    uint32_t *tile = sm;
+    const int tid = threadIdx.x;
+    const size_t row0 = (size_t)blockIdx.x * DOT_ROWS;
+    const int r = tid & (DOT_ROWS - 1), part = tid / DOT_ROWS;  // 4 column parts per row
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (uint32_t c0 = 0; c0 < width; c0 += DOT_COLS) {
+        __syncthreads();
+        for (int it = tid; it < DOT_ROWS * DOT_COLS; it += 256) {
+            const int rr = it / DOT_COLS, cc = it % DOT_COLS;
+            uint32_t v = 0;
+            if (row0 + rr < rows && c0 + cc < width) v = m[(row0 + rr) * width + c0 + cc];
+            tile[rr * (DOT_COLS + 1) + cc] = v;
+        }
+        __syncthreads();
+        for (int cc = part; cc < DOT_COLS && c0 + cc < width; cc += 4) {
+            const uint32_t v = tile[r * (DOT_COLS + 1) + cc];
+            const uint4 a = __ldg(apow + c0 + cc);
+            acc[0] = bb::add(acc[0], bb::mmul(v, a.x));
+            acc[1] = bb::add(acc[1], bb::mmul(v, a.y));
+            acc[2] = bb::add(acc[2], bb::mmul(v, a.z));
+            acc[3] = bb::add(acc[3], bb::mmul(v, a.w));
+        }
+    }
+    __syncthreads();
+    uint32_t *red = sm;  // reuse: [part][row][4]
+    for (int k = 0; k < 4; k++) red[(part * DOT_ROWS + r) * 4 + k] = acc[k];
+    __syncthreads();
+    if (part == 0 && row0 + r < rows) {
+        uint32_t o[4];
+        for (int k = 0; k < 4; k++) {
+            uint32_t s = red[r * 4 + k];
+            for (int pp = 1; pp < 4; pp++) s = bb::add(s, red[(pp * DOT_ROWS + r) * 4 + k]);
+            o[k] = s;
+        }
+        out[row0 + r] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+}  // namespace fold

@@ -1,0 +1,267 @@
+// hash.cuh -- Blake3 row hashing and the 2-to-1 Blake3 tree (sm_100a).
+//
+// Stands in for BFMmcs::commit (basic/src/mmcs/bf_mmcs.rs:23).  Construction ([MEM] Plonky3
+// FieldMerkleTreeMmcs<Val, u8, SerializingHasher32<Blake3>, CompressionFunctionFromHasher<u8,Blake3,2,32>, 32>,
+// the shape sketched in the commented-out uni-stark/tests/mul_air.rs:284-287):
+//   leaf digest  = Blake3( canonical-u32 little-endian bytes of the row(s) )      (plain hash mode)
+//   parent       = Blake3( left || right )                                        (plain 64-byte hash)
+// Blake3 itself is the function the reference uses in basic/src/challenger/mod.rs:35-39 and pins with
+// KATs in scripts/src/hashes/blake3.rs:537-587.
+//
+// The compression function runs entirely in registers, one leaf per thread.  Message words are staged
+// through shared memory: the CTA reads row segments coalesced (consecutive threads -> consecutive words of
+// one row), converts Montgomery -> canonical once, and each thread then reads its own leaf's words with a
+// conflict-free stride (odd pitch).
+#pragma once
+#include "field.cuh"
+
+namespace b3 {
+
+enum : uint32_t { CHUNK_START = 1, CHUNK_END = 2, PARENT = 4, ROOT = 8 };
+
+TS_D uint32_t rotr(uint32_t x, int n) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(x, x, n);
+#else
+    return (x >> n) | (x << (32 - n));
+#endif
+}
+
+#define TS_B3_G(a, b, c, d, mx, my) \
+    a = a + b + (mx);               \
+    d = rotr(d ^ a, 16);            \
+    c = c + d;                      \
+    b = rotr(b ^ c, 12);            \
+    a = a + b + (my);               \
+    d = rotr(d ^ a, 8);             \
+    c = c + d;                      \
+    b = rotr(b ^ c, 7);
+
+// message schedule: word index used at (round, slot), i.e. the permutation applied r times
+struct Sched {
+    int s[7][16];
+    constexpr Sched() : s{} {
+        const int perm[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
+        for (int i = 0; i < 16; i++) s[0][i] = i;
+        for (int r = 1; r < 7; r++)
+            for (int i = 0; i < 16; i++) s[r][i] = s[r - 1][perm[i]];
+    }
+};
+
+// cv <- first 8 words of compress(cv, m, counter, block_len, flags)
+TS_D void compress(uint32_t (&cv)[8], const uint32_t (&m)[16], uint32_t counter, uint32_t block_len,
+                   uint32_t flags) {
+    constexpr Sched S{};
+    uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
+    uint32_t s8 = 0x6A09E667u, s9 = 0xBB67AE85u, s10 = 0x3C6EF372u, s11 = 0xA54FF53Au;
+    uint32_t s12 = counter, s13 = 0u, s14 = block_len, s15 = flags;
+    TS_UNROLL
+    for (int r = 0; r < 7; r++) {
+        TS_B3_G(s0, s4, s8, s12, m[S.s[r][0]], m[S.s[r][1]])
+        TS_B3_G(s1, s5, s9, s13, m[S.s[r][2]], m[S.s[r][3]])
+        TS_B3_G(s2, s6, s10, s14, m[S.s[r][4]], m[S.s[r][5]])
+        TS_B3_G(s3, s7, s11, s15, m[S.s[r][6]], m[S.s[r][7]])
+        TS_B3_G(s0, s5, s10, s15, m[S.s[r][8]], m[S.s[r][9]])
+        TS_B3_G(s1, s6, s11, s12, m[S.s[r][10]], m[S.s[r][11]])
+        TS_B3_G(s2, s7, s8, s13, m[S.s[r][12]], m[S.s[r][13]])
+        TS_B3_G(s3, s4, s9, s14, m[S.s[r][14]], m[S.s[r][15]])
+    }
+    cv[0] = s0 ^ s8; cv[1] = s1 ^ s9; cv[2] = s2 ^ s10; cv[3] = s3 ^ s11;
+    cv[4] = s4 ^ s12; cv[5] = s5 ^ s13; cv[6] = s6 ^ s14; cv[7] = s7 ^ s15;
+}
+TS_D void iv(uint32_t (&cv)[8]) {
+    cv[0] = 0x6A09E667u; cv[1] = 0xBB67AE85u; cv[2] = 0x3C6EF372u; cv[3] = 0xA54FF53Au;
+    cv[4] = 0x510E527Fu; cv[5] = 0x9B05688Cu; cv[6] = 0x1F83D9ABu; cv[7] = 0x5BE0CD19u;
+}
+// out = Blake3 parent-style compression of (l || r) with the given flags and IV key
+TS_D void compress_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t flags, uint32_t (&out)[8]) {
+    uint32_t m[16];
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) { m[i] = l[i]; m[8 + i] = r[i]; }
+    iv(out);
+    compress(out, m, 0, 64, flags);
+}
+
+// ---- leaf hashing ---------------------------------------------------------------------------------
+constexpr int MAX_SEG = 8;
+struct Segments {
+    const uint32_t *ptr[MAX_SEG];
+    uint32_t width[MAX_SEG];
+    uint32_t shift[MAX_SEG];  // row = leaf >> shift
+    int n;
+    uint32_t total_words;
+};
+constexpr int LEAVES_PER_CTA = 128;
+constexpr int PIECE_WORDS = 64;          // words staged per leaf per step (4 Blake3 blocks)
+constexpr int PITCH = PIECE_WORDS + 1;   // odd pitch: thread l reading word j hits bank (l + j) mod 32
+constexpr int MAX_STACK = 6;             // up to 64 chunks = 64 KiB per leaf
+
+// digests[leaf][8] = Blake3(concat_s row_s[leaf >> shift_s] as canonical LE u32).  monty: inputs are
+// Montgomery form and are converted while staging.
+__global__ void __launch_bounds__(LEAVES_PER_CTA) hash_leaves_kernel(Segments sg, size_t n_leaves, int monty,
+                                                                     uint32_t *digests) {
+    TS_DYN_SMEM(uint32_t, stage);
+    const int tid = threadIdx.x;
+    const size_t leaf0 = (size_t)blockIdx.x * LEAVES_PER_CTA;
+    const size_t leaf = leaf0 + tid;
+    const uint32_t total_blocks = sg.total_words == 0 ? 1u : (sg.total_words + 15u) / 16u;
+    uint32_t cv[8];
+    uint32_t stack[MAX_STACK][8];
+    int sp = 0;
+    b3::iv(cv);
+    for (uint32_t c0 = 0; c0 < total_blocks * 16u; c0 += PIECE_WORDS) {
+        // cooperative, coalesced staging of words [c0, c0+PIECE) of LEAVES_PER_CTA leaves
+        __syncthreads();
+        for (int it = tid; it < LEAVES_PER_CTA * PIECE_WORDS; it += LEAVES_PER_CTA) {
+            const int l = it / PIECE_WORDS, j = it % PIECE_WORDS;
+            const uint32_t c = c0 + j;
+            uint32_t v = 0;
+            if (c < sg.total_words && leaf0 + l < n_leaves) {
+                uint32_t off = c;
+                int s = 0;
+                while (off >= sg.width[s]) { off -= sg.width[s]; s++; }
+                v = sg.ptr[s][(size_t)((leaf0 + l) >> sg.shift[s]) * sg.width[s] + off];
+                if (monty) v = bb::from_monty(v);
+            }
+            stage[l * PITCH + j] = v;
+        }
+        __syncthreads();
+        if (leaf < n_leaves) {
+            for (int bi = 0; bi < PIECE_WORDS / 16; bi++) {
+                const uint32_t blk = c0 / 16 + bi;
+                if (blk >= total_blocks) break;
+                uint32_t m[16];
+                TS_UNROLL
+                for (int i = 0; i < 16; i++) m[i] = stage[tid * PITCH + bi * 16 + i];
+                const uint32_t in_chunk = blk & 15u, chunk = blk >> 4;
+                const bool last = (blk + 1 == total_blocks);
+                uint32_t flags = (in_chunk == 0 ? CHUNK_START : 0u) | ((in_chunk == 15 || last) ? CHUNK_END : 0u);
+                const uint32_t rem = sg.total_words - blk * 16u;  // >= 1 unless the message is empty
+                const uint32_t block_len = sg.total_words == 0 ? 0u : (rem >= 16u ? 64u : rem * 4u);
+                if (last && sp == 0) flags |= ROOT;
+                compress(cv, m, chunk, block_len, flags);
+                if (last) {
+                    // fold the CV stack: parent(stack[top], cv) ..., ROOT on the final one
+                    while (sp > 0) {
+                        uint32_t out[8];
+                        sp--;
+                        compress_pair(stack[sp], cv, PARENT | (sp == 0 ? ROOT : 0u), out);
+                        TS_UNROLL
+                        for (int i = 0; i < 8; i++) cv[i] = out[i];
+                    }
+                } else if (in_chunk == 15) {
+                    // chunk finished and more input follows: merge completed subtrees (trailing zeros rule)
+                    uint32_t total_chunks = chunk + 1;
+                    while ((total_chunks & 1u) == 0) {
+                        uint32_t out[8];
+                        sp--;
+                        compress_pair(stack[sp], cv, PARENT, out);
+                        TS_UNROLL
+                        for (int i = 0; i < 8; i++) cv[i] = out[i];
+                        total_chunks >>= 1;
+                    }
+                    TS_UNROLL
+                    for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+                    sp++;
+                    b3::iv(cv);
+                }
+            }
+        }
+    }
+    if (leaf < n_leaves) {
+        TS_UNROLL
+        for (int i = 0; i < 8; i++) digests[leaf * 8 + i] = cv[i];
+    }
+}
+
+// Fast path for narrow single-segment leaves (<= 16 words, e.g. the FRI layers: 2 ext elements = 8 words):
+// one thread reads its own contiguous leaf, one compression.
+__global__ void __launch_bounds__(256) hash_leaves_small_kernel(const uint32_t *rows, uint32_t width, size_t n_leaves,
+                                                                int monty, uint32_t *digests) {
+    const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    uint32_t m[16];
+    TS_UNROLL
+    for (int i = 0; i < 16; i++) {
+        uint32_t v = 0;
+        if ((uint32_t)i < width) {
+            v = rows[leaf * width + i];
+            if (monty) v = bb::from_monty(v);
+        }
+        m[i] = v;
+    }
+    uint32_t cv[8];
+    iv(cv);
+    compress(cv, m, 0, width * 4u, CHUNK_START | CHUNK_END | ROOT);
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) digests[leaf * 8 + i] = cv[i];
+}
+
+// ---- tree ---------------------------------------------------------------------------------------
+// One CTA consumes 2*T child digests and produces up to `levels` layers above them (T, T/2, ... nodes),
+// every layer written to its own global array (openings need all of them).  Upper layers are reduced out
+// of shared memory.
+constexpr int TREE_T = 128;
+constexpr int TREE_MAX_LEVELS = 8;  // 2*128 = 2^8 children per CTA
+struct TreeLevels {
+    uint32_t *out[TREE_MAX_LEVELS];
+    int levels;
+};
+constexpr int NODE_PITCH = 9;
+__global__ void __launch_bounds__(TREE_T) tree_reduce_kernel(const uint32_t *children, size_t n_children,
+                                                             TreeLevels lv) {
+    TS_DYN_SMEM(uint32_t, nodes);  // TREE_T * NODE_PITCH words
+    const int tid = threadIdx.x;
+    const size_t parent0 = (size_t)blockIdx.x * TREE_T;
+    size_t n_par = n_children / 2;
+    uint32_t l[8], r[8], o[8];
+    {
+        const size_t pidx = parent0 + tid;
+        if (pidx < n_par) {
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) { l[i] = children[pidx * 16 + i]; r[i] = children[pidx * 16 + 8 + i]; }
+            compress_pair(l, r, CHUNK_START | CHUNK_END | ROOT, o);
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) { lv.out[0][pidx * 8 + i] = o[i]; nodes[tid * NODE_PITCH + i] = o[i]; }
+        }
+    }
+    int width = TREE_T;
+    for (int level = 1; level < lv.levels; level++) {
+        __syncthreads();
+        width >>= 1;
+        n_par >>= 1;
+        const size_t pidx = (parent0 >> level) + tid;
+        const bool act = tid < width && pidx < n_par;
+        if (act) {
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) {
+                l[i] = nodes[(2 * tid) * NODE_PITCH + i];
+                r[i] = nodes[(2 * tid + 1) * NODE_PITCH + i];
+            }
+            compress_pair(l, r, CHUNK_START | CHUNK_END | ROOT, o);
+        }
+        __syncthreads();
+        if (act) {
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) { lv.out[level][pidx * 8 + i] = o[i]; nodes[tid * NODE_PITCH + i] = o[i]; }
+        }
+    }
+}
+
+// P3 injection layer: out[i] = H( H(prev[2i] || prev[2i+1]) || rows_digest[i] )
+__global__ void compress_inject_kernel(const uint32_t *children, const uint32_t *rows_digest, size_t n_par,
+                                       uint32_t *out) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_par) return;
+    uint32_t l[8], r[8], o[8], o2[8];
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) { l[i] = children[p * 16 + i]; r[i] = children[p * 16 + 8 + i]; }
+    compress_pair(l, r, CHUNK_START | CHUNK_END | ROOT, o);
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = rows_digest[p * 8 + i];
+    compress_pair(o, r, CHUNK_START | CHUNK_END | ROOT, o2);
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) out[p * 8 + i] = o2[i];
+}
+
+}  // namespace b3

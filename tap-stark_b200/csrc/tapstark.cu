@@ -1,0 +1,1144 @@
+// tapstark.cu -- context, planning and the extern "C" surface of libtapstark_b200.so (see include/tapstark.h).
+//
+// Device work is enqueued on one stream per context; nothing here computes field/hash results on the host
+// except the Fiat-Shamir challenger and the verifier-side Merkle check, which are host code in the
+// reference too.
+#include "../../include/tapstark.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fold.cuh"
+#include "hash.cuh"
+#include "host_side.h"
+#include "ntt.cuh"
+
+// ------------------------------------------------------------------------------------------------ structs
+struct ts_matrix {
+    ts_ctx *ctx;
+    uint32_t *d;
+    size_t rows, width;
+    bool owned;
+};
+
+struct ts_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int num_sms = 148;
+    uint2 *tw_small = nullptr;
+    uint2 *tw_big = nullptr;
+    int big_log = 0;
+    uint32_t *fold_tlo = nullptr;
+    std::map<std::tuple<int, int, int, uint32_t>, std::pair<uint2 *, uint2 *>> coset_tabs;
+    uint32_t *scratch = nullptr;
+    size_t scratch_words = 0;
+    // stats
+    bool profiling = false;
+    double ms[TS_K_COUNT] = {0};
+    uint64_t launches[TS_K_COUNT] = {0};
+    uint64_t total_launches = 0;
+    struct Pending { cudaEvent_t a, b; int kind; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+struct ts_tree {
+    ts_ctx *ctx;
+    std::vector<ts_matrix *> mats;
+    bool own_mats;
+    int layout;
+    std::vector<size_t> order;
+    size_t hmax;
+    unsigned lmax;
+    uint32_t *digests;               // all layers, 8 words per node
+    std::vector<size_t> layer_off;   // in nodes
+};
+
+#define TS_FAIL(ctx, code, msg)      \
+    do {                             \
+        (ctx)->err = (msg);          \
+        return (code);               \
+    } while (0)
+#define TS_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return TS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+#define TS_TRY(expr)                  \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != TS_OK) return rc_; \
+    } while (0)
+
+namespace {
+
+struct KScope {  // counts a kernel launch and, when profiling, brackets it with events on the ctx stream
+    ts_ctx *c;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KScope(ts_ctx *c_, int kind_) : c(c_), kind(kind_) {
+        c->launches[kind]++;
+        c->total_launches++;
+        if (c->profiling) {
+            a = get();
+            b = get();
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    cudaEvent_t get() {
+        if (!c->ev_pool.empty()) {
+            cudaEvent_t e = c->ev_pool.back();
+            c->ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ~KScope() {
+        if (c->profiling) {
+            cudaEventRecord(b, c->stream);
+            c->pending.push_back({a, b, kind});
+        }
+    }
+};
+
+int check_launch(ts_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        c->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return TS_ERR_CUDA;
+    }
+    return TS_OK;
+}
+
+int log2_strict(size_t x) {
+    int l = 0;
+    while (((size_t)1 << l) < x) l++;
+    return (((size_t)1 << l) == x) ? l : -1;
+}
+int log2_ceil(size_t x) {
+    int l = 0;
+    while (((size_t)1 << l) < x) l++;
+    return l;
+}
+uint32_t h_to_monty(uint32_t x) { return (uint32_t)((((uint64_t)x) << 32) % bb::P); }
+uint32_t h_from_monty(uint32_t x) { return bb::cmul(x, bb::cinv(bb::MONTY_ONE)); }
+
+int ensure_scratch(ts_ctx *c, size_t words) {
+    if (c->scratch_words >= words) return TS_OK;
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_words = 0;
+    TS_CUDA(c, cudaMalloc((void **)&c->scratch, words * 4));
+    c->scratch_words = words;
+    return TS_OK;
+}
+
+int gen_twiddles(ts_ctx *c, uint2 *out, int log) {
+    ntt::RootPows rp;
+    uint32_t r = bb::two_adic_generator(log);
+    for (int k = 0; k < 28; k++) {
+        rp.v[k] = h_to_monty(r);
+        r = bb::cmul(r, r);
+    }
+    const uint32_t n = 1u << log;
+    KScope ks(c, TS_K_MISC);
+    auto kfn = ntt::gen_twiddles_kernel;
+    TS_LAUNCH(kfn, (n + 255) / 256, 256, 0, c->stream, out, log, rp);
+    return check_launch(c, "gen_twiddles_kernel");
+}
+
+int ensure_big(ts_ctx *c, int log) {
+    if (c->tw_big && c->big_log >= log) return TS_OK;
+    if (c->tw_big) {
+        TS_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->tw_big);
+        c->tw_big = nullptr;
+    }
+    TS_CUDA(c, cudaMalloc((void **)&c->tw_big, sizeof(uint2) << log));
+    c->big_log = log;
+    return gen_twiddles(c, c->tw_big, log);
+}
+
+// lanes of a tile: K = Bt x Ct, all powers of two
+struct Lanes {
+    int logBt, logCt, pad;
+};
+Lanes choose_lanes(int d, size_t w, int batch_bits, size_t max_tile_words) {
+    int logKmax = 0;
+    while (logKmax < 6 && (((size_t)2 << logKmax) << d) <= max_tile_words) logKmax++;
+    Lanes l;
+    l.logCt = std::min(log2_ceil(w), logKmax);
+    l.logBt = std::min(logKmax - l.logCt, batch_bits);
+    const int K = 1 << (l.logBt + l.logCt);
+    l.pad = K == 1 ? 0 : (K >= 32 ? 1 : 32 / K);
+    return l;
+}
+
+constexpr size_t kTileWords = 16384;
+
+// one in-place (or src->dst) DIF digit pass over rows of `bits_total` index bits
+int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, size_t w, int d, int lo_bits,
+                int hi_bits, bool has_scale, uint2 scale) {
+    ntt::PassParams p;
+    p.src = src;
+    p.dst = dst;
+    p.width = (uint32_t)w;
+    p.d = d;
+    p.lo_bits = lo_bits;
+    p.hi_bits = hi_bits;
+    p.batch_lo = lo_bits > 0;
+    const Lanes ln = choose_lanes(d, w, p.batch_lo ? lo_bits : hi_bits, kTileWords);
+    p.logBt = ln.logBt;
+    p.logCt = ln.logCt;
+    p.pad = ln.pad;
+    p.n_col_slices = (uint32_t)((w + ((size_t)1 << ln.logCt) - 1) >> ln.logCt);
+    p.post_tw = lo_bits > 0;
+    p.big_log = c->big_log;
+    p.tw_shift = p.post_tw ? c->big_log - (lo_bits + d) : 0;
+    p.tw_small = c->tw_small;
+    p.tw_big = c->tw_big;
+    p.has_scale = has_scale;
+    p.scale = scale;
+    size_t tiles = p.batch_lo ? (((size_t)1 << hi_bits) << (lo_bits - ln.logBt))
+                              : ((((size_t)1 << hi_bits) + ((size_t)1 << ln.logBt) - 1) >> ln.logBt);
+    const size_t blocks = tiles * p.n_col_slices;
+    const size_t smem = ((size_t)((1 << d) + ln.pad) << (ln.logBt + ln.logCt)) * 4;
+    KScope ks(c, TS_K_NTT_PASS);
+    if (inverse) {
+        auto kfn = ntt::ntt_pass_kernel<true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, 256, smem, c->stream, p);
+    } else {
+        auto kfn = ntt::ntt_pass_kernel<false>;
+        TS_LAUNCH(kfn, (unsigned)blocks, 256, smem, c->stream, p);
+    }
+    return check_launch(c, "ntt_pass_kernel");
+}
+
+std::vector<int> split_digits(int m) {
+    std::vector<int> d;
+    if (m <= 0) return d;
+    const int D = (m + ntt::MAX_DIGIT - 1) / ntt::MAX_DIGIT;
+    for (int i = 0; i < D; i++) d.push_back(m / D + (i < m % D ? 1 : 0));
+    return d;
+}
+
+// all digits of a full transform, top-down, in place on `data` (first pass may read `src`).
+// Output is in bit-reversed row order.
+int full_transform(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *data, size_t w, int m) {
+    const std::vector<int> dg = split_digits(m);
+    if (dg.size() > 1) TS_TRY(ensure_big(c, m));
+    int used = 0;
+    for (size_t i = 0; i < dg.size(); i++) {
+        const int lo_bits = m - used - dg[i];
+        const bool last = i + 1 == dg.size();
+        uint2 scale = make_uint2(0, 0);
+        if (inverse && last) {
+            const uint32_t ninv = bb::cinv((uint32_t)(((uint64_t)1 << m) % bb::P));
+            scale = make_uint2(ninv, bb::cshoup_prime(ninv));
+        }
+        TS_TRY(launch_pass(c, inverse, i == 0 ? src : data, data, w, dg[i], lo_bits, used, inverse && last, scale));
+        used += dg[i];
+    }
+    return TS_OK;
+}
+
+int get_coset_tables(ts_ctx *c, int m, int b, int d, uint32_t shift_monty, uint2 **pre, uint2 **lane) {
+    auto key = std::make_tuple(m, b, d, shift_monty);
+    auto it = c->coset_tabs.find(key);
+    if (it != c->coset_tabs.end()) {
+        *pre = it->second.first;
+        *lane = it->second.second;
+        return TS_OK;
+    }
+    const int klo = m - d;
+    uint2 *p = nullptr, *l = nullptr;
+    TS_CUDA(c, cudaMalloc((void **)&p, (sizeof(uint2) << d) << b));
+    TS_CUDA(c, cudaMalloc((void **)&l, (sizeof(uint2) << klo) << b));
+    const uint32_t wN = h_to_monty(bb::two_adic_generator(m + b));
+    const uint32_t ninv = h_to_monty(bb::cinv((uint32_t)(((uint64_t)1 << m) % bb::P)));
+    const uint32_t total = ((1u << d) + (1u << klo)) << b;
+    {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = ntt::gen_coset_tables_kernel;
+        TS_LAUNCH(kfn, (total + 255) / 256, 256, 0, c->stream, p, l, d, klo, b, shift_monty, wN, ninv);
+    }
+    TS_TRY(check_launch(c, "gen_coset_tables_kernel"));
+    c->coset_tabs[key] = {p, l};
+    *pre = p;
+    *lane = l;
+    return TS_OK;
+}
+
+// dst (n << b) x w  <-  committed-order coset LDE of src (n x w)
+int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty,
+                  uint32_t *dst) {
+    const int m = log2_strict(n);
+    if (m < 0 || w == 0 || m + (int)b > 27) TS_FAIL(c, TS_ERR_ARG, "lde: rows must be a power of two, rows<<added_bits <= 2^27");
+    if (m == 0) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = ntt::broadcast_row_kernel;
+        TS_LAUNCH(kfn, 64, 256, 0, c->stream, src, dst, (size_t)1 << b, (uint32_t)w);
+        return check_launch(c, "broadcast_row_kernel");
+    }
+    const std::vector<int> dg = split_digits(m);
+    const size_t D = dg.size();
+    const int dK = dg[D - 1];
+    const int klo = m - dK;
+    if (D > 1) {
+        TS_TRY(ensure_big(c, m));
+        TS_TRY(ensure_scratch(c, n * w));
+    }
+    uint2 *pre, *lane;
+    TS_TRY(get_coset_tables(c, m, (int)b, dK, shift_monty, &pre, &lane));
+    // inverse passes over the top digits
+    int used = 0;
+    for (size_t i = 0; i + 1 < D; i++) {
+        const int lo_bits = m - used - dg[i];
+        TS_TRY(launch_pass(c, true, i == 0 ? src : c->scratch, c->scratch, w, dg[i], lo_bits, used, false,
+                           make_uint2(0, 0)));
+        used += dg[i];
+    }
+    // middle kernel
+    {
+        ntt::MidParams p;
+        p.src = D > 1 ? c->scratch : src;
+        p.dst = dst;
+        p.width = (uint32_t)w;
+        p.d = dK;
+        p.klo_bits = klo;
+        p.b = (int)b;
+        const Lanes ln = choose_lanes(dK, w, klo, kTileWords);
+        p.logBt = ln.logBt;
+        p.logCt = ln.logCt;
+        p.pad = ln.pad;
+        p.n_col_slices = (uint32_t)((w + ((size_t)1 << ln.logCt) - 1) >> ln.logCt);
+        p.big_log = c->big_log;
+        p.tw_shift = klo > 0 ? c->big_log - m : 0;
+        p.tw_small = c->tw_small;
+        p.tw_big = c->tw_big;
+        p.pre_tab = pre;
+        p.lane_tab = lane;
+        const size_t blocks = ((size_t)1 << (klo - ln.logBt)) * p.n_col_slices;
+        const int K = 1 << (ln.logBt + ln.logCt);
+        const size_t smem = (size_t)2 * K * ((1 << dK) + ln.pad) * 4 + (size_t)K * sizeof(uint2);
+        KScope ks(c, TS_K_LDE_MID);
+        auto kfn = ntt::lde_mid_kernel;
+        TS_LAUNCH(kfn, (unsigned)blocks, 512, smem, c->stream, p);
+        TS_TRY(check_launch(c, "lde_mid_kernel"));
+    }
+    // forward passes over the remaining digits, all cosets at once
+    used = 0;
+    for (size_t i = 0; i + 1 < D; i++) {
+        const int lo_bits = klo - used - dg[i];
+        const int hi_bits = m + (int)b - lo_bits - dg[i];
+        TS_TRY(launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0)));
+        used += dg[i];
+    }
+    return TS_OK;
+}
+
+int new_matrix(ts_ctx *c, size_t rows, size_t width, ts_matrix **out) {
+    ts_matrix *m = new ts_matrix{c, nullptr, rows, width, true};
+    cudaError_t e = cudaMalloc((void **)&m->d, std::max<size_t>(rows * width, 1) * 4);
+    if (e != cudaSuccess) {
+        delete m;
+        c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return TS_ERR_CUDA;
+    }
+    *out = m;
+    return TS_OK;
+}
+
+int bitrev_rows(ts_ctx *c, const uint32_t *in, uint32_t *out, int log_h, size_t w) {
+    KScope ks(c, TS_K_MISC);
+    const size_t total = ((size_t)1 << log_h) * w;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
+    auto kfn = ntt::bitrev_rows_kernel;
+    TS_LAUNCH(kfn, blocks, 256, 0, c->stream, in, out, log_h, (uint32_t)w);
+    return check_launch(c, "bitrev_rows_kernel");
+}
+
+// ---- hashing ------------------------------------------------------------------------------------
+int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::vector<uint32_t> &shifts,
+              size_t n_leaves, uint32_t *digests) {
+    if (mats.size() > (size_t)b3::MAX_SEG) TS_FAIL(c, TS_ERR_ARG, "mmcs: more than 8 matrices hashed into one layer");
+    if (mats.size() == 1 && shifts[0] == 0 && mats[0]->width <= 16) {
+        KScope ks(c, TS_K_HASH_LEAVES);
+        auto kfn = b3::hash_leaves_small_kernel;
+        TS_LAUNCH(kfn, (unsigned)((n_leaves + 255) / 256), 256, 0, c->stream, (const uint32_t *)mats[0]->d,
+                  (uint32_t)mats[0]->width, n_leaves, 1, digests);
+        return check_launch(c, "hash_leaves_small_kernel");
+    }
+    b3::Segments sg;
+    sg.n = (int)mats.size();
+    sg.total_words = 0;
+    for (int i = 0; i < b3::MAX_SEG; i++) {
+        sg.ptr[i] = nullptr;
+        sg.width[i] = 0xffffffffu;  // sentinel: the segment walk never runs past the last real one
+        sg.shift[i] = 0;
+    }
+    for (size_t i = 0; i < mats.size(); i++) {
+        sg.ptr[i] = mats[i]->d;
+        sg.width[i] = (uint32_t)mats[i]->width;
+        sg.shift[i] = shifts[i];
+        sg.total_words += (uint32_t)mats[i]->width;
+    }
+    if ((sg.total_words + 255) / 256 > (1u << b3::MAX_STACK)) TS_FAIL(c, TS_ERR_ARG, "mmcs: leaf wider than 64 KiB");
+    KScope ks(c, TS_K_HASH_LEAVES);
+    auto kfn = b3::hash_leaves_kernel;
+    const size_t smem = (size_t)b3::LEAVES_PER_CTA * b3::PITCH * 4;
+    TS_LAUNCH(kfn, (unsigned)((n_leaves + b3::LEAVES_PER_CTA - 1) / b3::LEAVES_PER_CTA), b3::LEAVES_PER_CTA, smem,
+              c->stream, sg, n_leaves, 1, digests);
+    return check_launch(c, "hash_leaves_kernel");
+}
+
+int build_tree(ts_ctx *c, ts_tree *t) {
+    const size_t k = t->mats.size();
+    size_t n_first = 0;
+    if (t->layout == TS_LAYOUT_PADDED) n_first = k;
+    else
+        while (n_first < k && t->mats[t->order[n_first]]->rows == t->hmax) n_first++;
+    {
+        std::vector<const ts_matrix *> ms;
+        std::vector<uint32_t> sh;
+        for (size_t q = 0; q < n_first; q++) {
+            const ts_matrix *m = t->mats[t->order[q]];
+            ms.push_back(m);
+            sh.push_back(t->lmax - (unsigned)log2_strict(m->rows));
+        }
+        TS_TRY(hash_rows(c, ms, sh, t->hmax, t->digests));
+    }
+    size_t next_mat = n_first;
+    unsigned l = 1;
+    while (l <= t->lmax) {
+        const size_t len = t->hmax >> l;
+        size_t inj0 = next_mat;
+        if (t->layout == TS_LAYOUT_P3_INJECT)
+            while (next_mat < k && t->mats[t->order[next_mat]]->rows == len) next_mat++;
+        const uint32_t *children = t->digests + t->layer_off[l - 1] * 8;
+        if (next_mat > inj0) {
+            std::vector<const ts_matrix *> ms;
+            std::vector<uint32_t> sh;
+            for (size_t q = inj0; q < next_mat; q++) {
+                ms.push_back(t->mats[t->order[q]]);
+                sh.push_back(0);
+            }
+            TS_TRY(ensure_scratch(c, len * 8));
+            TS_TRY(hash_rows(c, ms, sh, len, c->scratch));
+            KScope ks(c, TS_K_TREE);
+            auto kfn = b3::compress_inject_kernel;
+            TS_LAUNCH(kfn, (unsigned)((len + 127) / 128), 128, 0, c->stream, children, (const uint32_t *)c->scratch,
+                      len, t->digests + t->layer_off[l] * 8);
+            TS_TRY(check_launch(c, "compress_inject_kernel"));
+            l++;
+            continue;
+        }
+        // as many plain levels as possible in one launch (stop before the next injection layer)
+        int levels = 0;
+        while (levels < b3::TREE_MAX_LEVELS && l + levels <= t->lmax) {
+            if (levels > 0 && t->layout == TS_LAYOUT_P3_INJECT && next_mat < k &&
+                t->mats[t->order[next_mat]]->rows == (t->hmax >> (l + levels)))
+                break;
+            levels++;
+        }
+        b3::TreeLevels lv;
+        lv.levels = levels;
+        for (int i = 0; i < b3::TREE_MAX_LEVELS; i++)
+            lv.out[i] = i < levels ? t->digests + t->layer_off[l + i] * 8 : nullptr;
+        const size_t n_children = t->hmax >> (l - 1);
+        KScope ks(c, TS_K_TREE);
+        auto kfn = b3::tree_reduce_kernel;
+        TS_LAUNCH(kfn, (unsigned)((n_children / 2 + b3::TREE_T - 1) / b3::TREE_T), b3::TREE_T,
+                  (size_t)b3::TREE_T * b3::NODE_PITCH * 4, c->stream, children, n_children, lv);
+        TS_TRY(check_launch(c, "tree_reduce_kernel"));
+        l += levels;
+    }
+    return TS_OK;
+}
+
+int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, int take_ownership,
+                uint8_t root[32], ts_tree **out, bool sync_root) {
+    if (n_mats == 0) TS_FAIL(ctx, TS_ERR_ARG, "mmcs: no matrices");
+    ts_tree *t = new ts_tree;
+    t->ctx = ctx;
+    t->mats.assign(mats, mats + n_mats);
+    t->own_mats = take_ownership != 0;
+    t->layout = layout;
+    t->digests = nullptr;
+    t->order.resize(n_mats);
+    for (size_t i = 0; i < n_mats; i++) t->order[i] = i;
+    std::stable_sort(t->order.begin(), t->order.end(),
+                     [&](size_t a, size_t b) { return mats[a]->rows > mats[b]->rows; });
+    t->hmax = mats[t->order[0]]->rows;
+    for (size_t i = 0; i < n_mats; i++)
+        if (log2_strict(mats[i]->rows) < 0) {
+            t->own_mats = false;
+            ts_tree_free(t);
+            TS_FAIL(ctx, TS_ERR_ARG, "mmcs: heights must be powers of two");
+        }
+    t->lmax = (unsigned)log2_strict(t->hmax);
+    size_t off = 0;
+    for (unsigned l = 0; l <= t->lmax; l++) {
+        t->layer_off.push_back(off);
+        off += t->hmax >> l;
+    }
+    cudaError_t e = cudaMalloc((void **)&t->digests, off * 32);
+    if (e != cudaSuccess) {
+        t->own_mats = false;
+        ts_tree_free(t);
+        TS_FAIL(ctx, TS_ERR_CUDA, std::string("cudaMalloc digests: ") + cudaGetErrorString(e));
+    }
+    int rc = build_tree(ctx, t);
+    if (rc == TS_OK && root) {
+        cudaError_t e2 = cudaMemcpyAsync(root, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToHost,
+                                         ctx->stream);
+        if (e2 == cudaSuccess && sync_root) e2 = cudaStreamSynchronize(ctx->stream);
+        if (e2 != cudaSuccess) {
+            ctx->err = std::string("root download: ") + cudaGetErrorString(e2);
+            rc = TS_ERR_CUDA;
+        }
+    }
+    if (rc != TS_OK) {
+        t->own_mats = false;
+        ts_tree_free(t);
+        return rc;
+    }
+    *out = t;
+    return TS_OK;
+}
+
+// host-side canonical EF helpers (transcript values; a handful per FRI round)
+void h_ef_mul(const uint32_t a[4], const uint32_t b[4], uint32_t o[4]) {
+    uint32_t r[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) r[i + j] = (uint32_t)((r[i + j] + (uint64_t)a[i] * b[j]) % bb::P);
+    for (int i = 0; i < 4; i++) o[i] = i < 3 ? (uint32_t)((r[i] + 11ull * r[i + 4]) % bb::P) : r[i];
+}
+
+int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t *addend, int log_h,
+                    const uint32_t beta_canon[4]) {
+    const uint32_t half = bb::cinv(2);
+    ef::E4 hb;
+    for (int i = 0; i < 4; i++) hb.c[i] = h_to_monty(bb::cmul(beta_canon[i], half));
+    const uint32_t g_inv = bb::cinv(bb::two_adic_generator(log_h + 1));
+    fold::InvRootPows rp;
+    uint32_t r = g_inv;
+    for (int k = 0; k < 28; k++) {
+        rp.v[k] = h_to_monty(r);
+        r = bb::cmul(r, r);
+    }
+    fold::ChunkDeltas dl;
+    const int Lh = log_h - 8;
+    for (int t = 0; t < 28; t++) {
+        uint32_t v = 1;
+        if (Lh > 0 && t < Lh) {
+            // bitrev(c+1) - bitrev(c) for c ending in t ones: + 2^(Lh-1-t) - sum_{k<t} 2^(Lh-1-k), mod 2h
+            int64_t delta = (int64_t)1 << (Lh - 1 - t);
+            for (int k = 0; k < t; k++) delta -= (int64_t)1 << (Lh - 1 - k);
+            const int64_t order = (int64_t)2 << log_h;
+            delta = ((delta % order) + order) % order;
+            v = bb::cpow(g_inv, (uint64_t)delta);
+        }
+        dl.v[t] = h_to_monty(v);
+    }
+    const size_t h = (size_t)1 << log_h;
+    unsigned blocks = 1;
+    if (log_h >= 8) blocks = (unsigned)std::min<size_t>(h >> 8, (size_t)c->num_sms * 8);
+    KScope ks(c, TS_K_FOLD);
+    auto kfn = fold::fold_ext_kernel;
+    TS_LAUNCH(kfn, blocks, fold::FOLD_T, 0, c->stream, (const uint4 *)in, (uint4 *)out, (const uint4 *)addend, log_h,
+              hb, rp, dl, (const uint32_t *)c->fold_tlo);
+    return check_launch(c, "fold_ext_kernel");
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int ts_is_device_build(void) {
+#ifdef TS_EMULATE
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+int ts_ctx_create(int device, void *stream, ts_ctx **out) {
+    if (!out) return TS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) return TS_ERR_CUDA;  // no GPU: fail loudly
+    if (cudaSetDevice(device) != cudaSuccess) return TS_ERR_CUDA;
+    ts_ctx *c = new ts_ctx;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+#ifndef TS_EMULATE
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return TS_ERR_CUDA;
+        }
+        c->own_stream = true;
+#endif
+    }
+    // kernels that need more than 48 KiB of dynamic shared memory
+    cudaFuncSetAttribute(ntt::ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(ntt::ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(ntt::lde_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    // small twiddle table w_4096^e and the fold's 256-entry low table, built once
+    bool ok = cudaMalloc((void **)&c->tw_small, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
+              cudaMalloc((void **)&c->fold_tlo, 256 * 4) == cudaSuccess;
+    if (ok) ok = gen_twiddles(c, c->tw_small, ntt::SMALL_LOG) == TS_OK;
+    if (ok) {
+        uint32_t tlo[256];
+        const uint32_t w512inv = bb::cinv(bb::two_adic_generator(9));
+        for (uint32_t t = 0; t < 256; t++) {
+            uint32_t r = 0;
+            for (int k = 0; k < 8; k++) r |= ((t >> k) & 1) << (7 - k);
+            tlo[t] = h_to_monty(bb::cpow(w512inv, r));
+        }
+        ok = cudaMemcpyAsync(c->fold_tlo, tlo, sizeof tlo, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        ts_ctx_destroy(c);
+        return TS_ERR_CUDA;
+    }
+    *out = c;
+    return TS_OK;
+}
+
+void ts_ctx_destroy(ts_ctx *c) {
+    if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->tw_small);
+    cudaFree(c->tw_big);
+    cudaFree(c->fold_tlo);
+    cudaFree(c->scratch);
+    for (auto &kv : c->coset_tabs) {
+        cudaFree(kv.second.first);
+        cudaFree(kv.second.second);
+    }
+    for (auto &p : c->pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+#ifndef TS_EMULATE
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+
+const char *ts_last_error(const ts_ctx *c) { return c ? c->err.c_str() : "null context"; }
+int ts_ctx_synchronize(ts_ctx *c) {
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TS_OK;
+}
+int ts_ctx_set_profiling(ts_ctx *c, int on) {
+    c->profiling = on != 0;
+    return TS_OK;
+}
+static void drain_pending(ts_ctx *c) {
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->ms[p.kind] += ms;
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
+int ts_ctx_reset_stats(ts_ctx *c) {
+    drain_pending(c);
+    for (int i = 0; i < TS_K_COUNT; i++) {
+        c->ms[i] = 0;
+        c->launches[i] = 0;
+    }
+    c->total_launches = 0;
+    return TS_OK;
+}
+int ts_ctx_get_stats(ts_ctx *c, int kind, double *ms, uint64_t *launches) {
+    if (kind < 0 || kind >= TS_K_COUNT) TS_FAIL(c, TS_ERR_ARG, "bad kernel kind");
+    drain_pending(c);
+    if (ms) *ms = c->ms[kind];
+    if (launches) *launches = c->launches[kind];
+    return TS_OK;
+}
+uint64_t ts_ctx_total_launches(const ts_ctx *c) { return c->total_launches; }
+
+// ---------------------------------------------------------------- matrices
+int ts_matrix_alloc(ts_ctx *c, size_t rows, size_t width, ts_matrix **out) { return new_matrix(c, rows, width, out); }
+int ts_matrix_from_host(ts_ctx *c, const uint32_t *host, size_t rows, size_t width, ts_matrix **out) {
+    TS_TRY(new_matrix(c, rows, width, out));
+    TS_CUDA(c, cudaMemcpyAsync((*out)->d, host, rows * width * 4, cudaMemcpyHostToDevice, c->stream));
+    return TS_OK;
+}
+int ts_matrix_from_device(ts_ctx *c, const uint32_t *dev, size_t rows, size_t width, ts_matrix **out) {
+    TS_TRY(new_matrix(c, rows, width, out));
+    TS_CUDA(c, cudaMemcpyAsync((*out)->d, dev, rows * width * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return TS_OK;
+}
+int ts_matrix_wrap_device(ts_ctx *c, uint32_t *dev, size_t rows, size_t width, ts_matrix **out) {
+    *out = new ts_matrix{c, dev, rows, width, false};
+    return TS_OK;
+}
+int ts_matrix_download(ts_ctx *c, const ts_matrix *m, size_t row0, size_t nrows, uint32_t *host) {
+    if (row0 + nrows > m->rows) TS_FAIL(c, TS_ERR_ARG, "download: row range out of bounds");
+    TS_CUDA(c, cudaMemcpyAsync(host, m->d + row0 * m->width, nrows * m->width * 4, cudaMemcpyDeviceToHost, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TS_OK;
+}
+uint32_t *ts_matrix_device_ptr(const ts_matrix *m) { return m->d; }
+size_t ts_matrix_rows(const ts_matrix *m) { return m->rows; }
+size_t ts_matrix_width(const ts_matrix *m) { return m->width; }
+void ts_matrix_free(ts_matrix *m) {
+    if (!m) return;
+    if (m->owned && m->d) {
+        cudaStreamSynchronize(m->ctx->stream);
+        cudaFree(m->d);
+    }
+    delete m;
+}
+static int monty_convert(ts_ctx *c, ts_matrix *m, int to) {
+    KScope ks(c, TS_K_MISC);
+    const size_t n = m->rows * m->width;
+    auto kfn = ntt::monty_convert_kernel;
+    TS_LAUNCH(kfn, (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream, m->d, n, to);
+    return check_launch(c, "monty_convert_kernel");
+}
+int ts_matrix_to_monty(ts_ctx *c, ts_matrix *m) { return monty_convert(c, m, 1); }
+int ts_matrix_from_monty(ts_ctx *c, ts_matrix *m) { return monty_convert(c, m, 0); }
+int ts_matrix_bit_reverse_rows(ts_ctx *c, const ts_matrix *m, ts_matrix **out) {
+    const int lh = log2_strict(m->rows);
+    if (lh < 0) TS_FAIL(c, TS_ERR_ARG, "bit_reverse_rows: height must be a power of two");
+    TS_TRY(new_matrix(c, m->rows, m->width, out));
+    return bitrev_rows(c, m->d, (*out)->d, lh, m->width);
+}
+
+// ---------------------------------------------------------------- DFT family
+int ts_coset_lde_batch(ts_ctx *c, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty, int natural_order,
+                       ts_matrix **out) {
+    ts_matrix *o = nullptr;
+    TS_TRY(new_matrix(c, evals->rows << added_bits, evals->width, &o));
+    int rc = lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, o->d);
+    if (rc == TS_OK && natural_order) {
+        ts_matrix *nat = nullptr;
+        rc = ts_matrix_bit_reverse_rows(c, o, &nat);
+        ts_matrix_free(o);
+        o = nat;
+    }
+    if (rc != TS_OK) {
+        ts_matrix_free(o);
+        return rc;
+    }
+    *out = o;
+    return TS_OK;
+}
+int ts_lde_batch(ts_ctx *c, const ts_matrix *evals, unsigned added_bits, ts_matrix **out) {
+    return ts_coset_lde_batch(c, evals, added_bits, bb::MONTY_ONE, 1, out);
+}
+static int plain_transform(ts_ctx *c, bool inverse, const ts_matrix *in, bool with_shift, uint32_t shift_monty,
+                           ts_matrix **out) {
+    const int m = log2_strict(in->rows);
+    if (m < 0 || m > 27) TS_FAIL(c, TS_ERR_ARG, "dft: height must be a power of two <= 2^27");
+    ts_matrix *work = nullptr;
+    TS_TRY(ts_matrix_from_device(c, in->d, in->rows, in->width, &work));
+    int rc = TS_OK;
+    if (with_shift) {
+        KScope ks(c, TS_K_MISC);
+        const size_t total = in->rows * in->width;
+        auto kfn = ntt::scale_rows_pow_kernel;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream,
+                  work->d, m, (uint32_t)in->width, shift_monty);
+        rc = check_launch(c, "scale_rows_pow_kernel");
+    }
+    if (rc == TS_OK) rc = full_transform(c, inverse, work->d, work->d, in->width, m);
+    ts_matrix *nat = nullptr;
+    if (rc == TS_OK) rc = ts_matrix_bit_reverse_rows(c, work, &nat);
+    ts_matrix_free(work);
+    if (rc != TS_OK) return rc;
+    *out = nat;
+    return TS_OK;
+}
+int ts_dft_batch(ts_ctx *c, const ts_matrix *coeffs, ts_matrix **out) {
+    return plain_transform(c, false, coeffs, false, 0, out);
+}
+int ts_idft_batch(ts_ctx *c, const ts_matrix *evals, ts_matrix **out) {
+    return plain_transform(c, true, evals, false, 0, out);
+}
+int ts_coset_dft_batch(ts_ctx *c, const ts_matrix *coeffs, uint32_t shift_monty, ts_matrix **out) {
+    return plain_transform(c, false, coeffs, true, shift_monty, out);
+}
+int ts_coset_lde_batch_host(ts_ctx *c, const uint32_t *evals_host, size_t rows, size_t width, unsigned added_bits,
+                            uint32_t shift_monty, int natural_order, uint32_t *out_host) {
+    ts_matrix *in = nullptr, *o = nullptr;
+    TS_TRY(ts_matrix_from_host(c, evals_host, rows, width, &in));
+    int rc = ts_coset_lde_batch(c, in, added_bits, shift_monty, natural_order, &o);
+    if (rc == TS_OK) rc = ts_matrix_download(c, o, 0, o->rows, out_host);
+    ts_matrix_free(in);
+    ts_matrix_free(o);
+    return rc;
+}
+
+// ---------------------------------------------------------------- MMCS
+int ts_mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, int take_ownership,
+                   uint8_t root[32], ts_tree **out) {
+    return mmcs_commit(ctx, mats, n_mats, layout, take_ownership, root, out, true);
+}
+size_t ts_tree_num_matrices(const ts_tree *t) { return t->mats.size(); }
+ts_matrix *ts_tree_matrix(const ts_tree *t, size_t i) { return i < t->mats.size() ? t->mats[i] : nullptr; }
+size_t ts_tree_depth(const ts_tree *t) { return t->lmax; }
+size_t ts_tree_max_height(const ts_tree *t) { return t->hmax; }
+int ts_mmcs_open_batch(ts_ctx *c, const ts_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out) {
+    if (index >= t->hmax) TS_FAIL(c, TS_ERR_ARG, "open_batch: index out of range");
+    size_t o = 0;
+    for (const ts_matrix *m : t->mats) {
+        const size_t row = index >> (t->lmax - (unsigned)log2_strict(m->rows));
+        TS_CUDA(c, cudaMemcpyAsync(rows_out + o, m->d + row * m->width, m->width * 4, cudaMemcpyDeviceToHost, c->stream));
+        o += m->width;
+    }
+    for (unsigned l = 0; l < t->lmax; l++) {
+        const size_t node = (index >> l) ^ 1;
+        TS_CUDA(c, cudaMemcpyAsync(path_out + 32 * l, t->digests + (t->layer_off[l] + node) * 8, 32,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    }
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TS_OK;
+}
+int ts_tree_layer(ts_ctx *c, const ts_tree *t, size_t layer, uint8_t *out, size_t *n_nodes) {
+    if (layer > t->lmax) TS_FAIL(c, TS_ERR_ARG, "tree_layer: no such layer");
+    const size_t n = t->hmax >> layer;
+    if (n_nodes) *n_nodes = n;
+    if (out) {
+        TS_CUDA(c, cudaMemcpyAsync(out, t->digests + t->layer_off[layer] * 8, n * 32, cudaMemcpyDeviceToHost, c->stream));
+        TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return TS_OK;
+}
+void ts_tree_free(ts_tree *t) {
+    if (!t) return;
+    if (t->digests) {
+        cudaStreamSynchronize(t->ctx->stream);
+        cudaFree(t->digests);
+    }
+    for (ts_matrix *m : t->mats)
+        if (t->own_mats) ts_matrix_free(m);
+    delete t;
+}
+int ts_mmcs_verify_batch(const size_t *heights, const size_t *widths, size_t k, int layout, size_t index,
+                         const uint32_t *rows_monty, const uint8_t *path, size_t depth, const uint8_t root[32]) {
+    if (k == 0) return TS_ERR_ARG;
+    std::vector<size_t> order(k), offs(k);
+    size_t o = 0;
+    for (size_t i = 0; i < k; i++) {
+        order[i] = i;
+        offs[i] = o;
+        o += widths[i];
+    }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return heights[a] > heights[b]; });
+    const size_t hmax = heights[order[0]];
+    if (((size_t)1 << depth) != hmax) return TS_ERR_ARG;
+    auto hash_group = [&](size_t q0, size_t q1, uint8_t out[32]) {
+        std::vector<uint8_t> buf;
+        for (size_t q = q0; q < q1; q++) {
+            const size_t m = order[q];
+            for (size_t cidx = 0; cidx < widths[m]; cidx++) {
+                const uint32_t v = h_from_monty(rows_monty[offs[m] + cidx]);
+                for (int b = 0; b < 4; b++) buf.push_back((uint8_t)(v >> (8 * b)));
+            }
+        }
+        hostb3::hash(buf.data(), buf.size(), out);
+    };
+    size_t n_first = 0;
+    if (layout == TS_LAYOUT_PADDED) n_first = k;
+    else
+        while (n_first < k && heights[order[n_first]] == hmax) n_first++;
+    uint8_t cur[32], pair[64];
+    hash_group(0, n_first, cur);
+    size_t next = n_first, len = hmax;
+    for (size_t l = 0; l < depth; l++) {
+        if (index & 1) {
+            memcpy(pair, path + 32 * l, 32);
+            memcpy(pair + 32, cur, 32);
+        } else {
+            memcpy(pair, cur, 32);
+            memcpy(pair + 32, path + 32 * l, 32);
+        }
+        hostb3::hash(pair, 64, cur);
+        index >>= 1;
+        len >>= 1;
+        const size_t inj0 = next;
+        if (layout == TS_LAYOUT_P3_INJECT)
+            while (next < k && heights[order[next]] == len) next++;
+        if (next > inj0) {
+            memcpy(pair, cur, 32);
+            hash_group(inj0, next, pair + 32);
+            hostb3::hash(pair, 64, cur);
+        }
+    }
+    return memcmp(cur, root, 32) == 0 ? TS_OK : TS_ERR_ARG;
+}
+
+// ---------------------------------------------------------------- challenger
+int ts_challenger_new(ts_challenger **out) {
+    *out = new ts_challenger;
+    return TS_OK;
+}
+int ts_challenger_clone(const ts_challenger *c, ts_challenger **out) {
+    *out = new ts_challenger(*c);
+    return TS_OK;
+}
+void ts_challenger_free(ts_challenger *c) { delete c; }
+void ts_challenger_observe(ts_challenger *c, const uint8_t word[4]) { c->observe(word); }
+void ts_challenger_observe_digest(ts_challenger *c, const uint8_t digest[32]) {
+    for (int i = 0; i < 8; i++) c->observe(digest + 4 * i);
+}
+uint32_t ts_challenger_sample_base(ts_challenger *c) { return c->sample_base(); }
+void ts_challenger_sample_ext(ts_challenger *c, uint32_t out[4]) {
+    for (int i = 0; i < 4; i++) out[i] = c->sample_base();
+}
+size_t ts_challenger_sample_bits(ts_challenger *c, unsigned bits, int ext) { return c->sample_bits(bits, ext != 0); }
+int ts_challenger_check_witness(ts_challenger *c, unsigned bits, uint32_t witness, int ext) {
+    return c->check_witness(bits, witness, ext != 0) ? 1 : 0;
+}
+int ts_challenger_grind(ts_challenger *c, unsigned bits, int ext, uint32_t *witness) {
+    for (uint32_t w = 0; w < 4096; w++) {
+        ts_challenger t(*c);
+        if (t.check_witness(bits, w, ext != 0)) {
+            c->check_witness(bits, w, ext != 0);
+            *witness = w;
+            return TS_OK;
+        }
+    }
+    return TS_ERR_NO_WITNESS;
+}
+
+// ---------------------------------------------------------------- fold
+int ts_fri_fold_ext(ts_ctx *c, const uint32_t *in_dev, size_t h, const uint32_t beta_monty[4], uint32_t *out_dev) {
+    const int lh = log2_strict(h);
+    if (lh < 0 || lh > 26) TS_FAIL(c, TS_ERR_ARG, "fold: h must be a power of two <= 2^26");
+    uint32_t beta[4];
+    for (int i = 0; i < 4; i++) beta[i] = h_from_monty(beta_monty[i]);
+    return fold_ext_launch(c, in_dev, out_dev, nullptr, lh, beta);
+}
+int ts_fri_fold_base(ts_ctx *c, const uint32_t *in_dev, size_t h, uint32_t beta_monty, uint32_t *out_dev) {
+    const int lh = log2_strict(h);
+    if (lh < 0 || lh > 26) TS_FAIL(c, TS_ERR_ARG, "fold: h must be a power of two <= 2^26");
+    const uint32_t hb = h_to_monty(bb::cmul(h_from_monty(beta_monty), bb::cinv(2)));
+    fold::InvRootPows rp;
+    uint32_t r = bb::cinv(bb::two_adic_generator(lh + 1));
+    for (int k = 0; k < 28; k++) {
+        rp.v[k] = h_to_monty(r);
+        r = bb::cmul(r, r);
+    }
+    KScope ks(c, TS_K_FOLD);
+    auto kfn = fold::fold_base_kernel;
+    TS_LAUNCH(kfn, (unsigned)std::min<size_t>((h + 255) / 256, (size_t)c->num_sms * 8), fold::FOLD_T, 0, c->stream,
+              (const uint2 *)in_dev, out_dev, lh, hb, rp);
+    return check_launch(c, "fold_base_kernel");
+}
+int ts_fri_fold_ext_host(ts_ctx *c, const uint32_t *in_host, size_t h, const uint32_t beta_monty[4],
+                         uint32_t *out_host) {
+    ts_matrix *in = nullptr, *o = nullptr;
+    TS_TRY(ts_matrix_from_host(c, in_host, 2 * h, 4, &in));
+    int rc = new_matrix(c, h, 4, &o);
+    if (rc == TS_OK) rc = ts_fri_fold_ext(c, in->d, h, beta_monty, o->d);
+    if (rc == TS_OK) rc = ts_matrix_download(c, o, 0, h, out_host);
+    ts_matrix_free(in);
+    ts_matrix_free(o);
+    return rc;
+}
+
+// ---------------------------------------------------------------- commit phase (fri/src/prover.rs:93-141)
+int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, unsigned log_blowup, ts_challenger *chal,
+                        uint8_t *commits, ts_tree **trees, uint32_t final_poly[4], size_t *rounds_out) {
+    if (n_inputs == 0) TS_FAIL(c, TS_ERR_ARG, "commit phase: no inputs");
+    for (size_t i = 0; i < n_inputs; i++) {
+        if (inputs[i]->width != 4 || log2_strict(inputs[i]->rows) < 0)
+            TS_FAIL(c, TS_ERR_ARG, "commit phase: inputs must be EF vectors (width 4) of power-of-two length");
+        if (i > 0 && inputs[i]->rows >= inputs[i - 1]->rows)
+            TS_FAIL(c, TS_ERR_ARG, "commit phase: inputs must be sorted by strictly descending length");
+    }
+    size_t len = inputs[0]->rows, next_in = 1, round = 0;
+    // current layer.  When prover data is kept, round 0 commits to a clone of the first input
+    // (`folded.clone()`, prover.rs:112) so every returned tree owns its layer; otherwise it is borrowed.
+    uint32_t *cur = inputs[0]->d;
+    bool cur_owned = false;
+    const size_t blowup = (size_t)1 << log_blowup;
+    int rc = TS_OK;
+    if (trees && len > blowup) {
+        uint32_t *cl = nullptr;
+        TS_CUDA(c, cudaMalloc((void **)&cl, len * 16));
+        cudaError_t e = cudaMemcpyAsync(cl, cur, len * 16, cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(cl);
+            TS_FAIL(c, TS_ERR_CUDA, std::string("clone first input: ") + cudaGetErrorString(e));
+        }
+        cur = cl;
+        cur_owned = true;
+    }
+    while (len > blowup) {
+        const size_t h = len / 2;
+        // leaves = RowMajorMatrix::new(folded.clone(), 2): h rows of 2 EF = 8 u32 (prover.rs:112)
+        ts_matrix *leaves = new ts_matrix{c, cur, h, 8, cur_owned};
+        ts_tree *tree = nullptr;
+        uint8_t root[32];
+        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, root, &tree, true);  // prover.rs:113
+        if (rc != TS_OK) {
+            ts_matrix_free(leaves);
+            cur = nullptr;
+            break;
+        }
+        // the tree now owns `leaves` (and the layer buffer when it was ours)
+        memcpy(commits + 32 * round, root, 32);
+        ts_challenger_observe_digest(chal, root);  // prover.rs:114
+        uint32_t beta[4];
+        ts_challenger_sample_ext(chal, beta);  // prover.rs:116
+        uint32_t *nf = nullptr;
+        cudaError_t e = cudaMalloc((void **)&nf, h * 16);
+        if (e != cudaSuccess) {
+            c->err = std::string("cudaMalloc folded: ") + cudaGetErrorString(e);
+            rc = TS_ERR_CUDA;
+        } else {
+            const uint32_t *addend = nullptr;
+            if (next_in < n_inputs && inputs[next_in]->rows == h) addend = inputs[next_in++]->d;  // prover.rs:124-126
+            rc = fold_ext_launch(c, cur, nf, addend, log2_strict(h), beta);  // prover.rs:119
+        }
+        cur = nullptr;
+        cur_owned = false;
+        if (rc != TS_OK || !trees) ts_tree_free(tree);  // synchronises the stream before freeing the layer
+        else trees[round] = tree;
+        if (rc != TS_OK) {
+            if (nf) cudaFree(nf);
+            break;
+        }
+        cur = nf;
+        cur_owned = true;
+        len = h;
+        round++;
+    }
+    if (rc == TS_OK) {
+        std::vector<uint32_t> tail(len * 4);
+        cudaError_t e = cudaMemcpyAsync(tail.data(), cur, len * 16, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            c->err = std::string("final layer download: ") + cudaGetErrorString(e);
+            rc = TS_ERR_CUDA;
+        } else {
+            for (int i = 0; i < 4; i++) final_poly[i] = h_from_monty(tail[i]);
+            for (size_t i = 1; i < len; i++)
+                if (memcmp(&tail[4 * i], &tail[0], 16) != 0) {  // prover.rs:130-134
+                    c->err = "commit phase: final layer is not constant (input not low-degree)";
+                    rc = TS_ERR_NOT_CONSTANT;
+                }
+        }
+    }
+    if (cur_owned && cur) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(cur);
+    }
+    if (rounds_out) *rounds_out = round;
+    return rc;
+}
+
+// ---------------------------------------------------------------- PCS
+int ts_pcs_commit(ts_ctx *c, ts_matrix *const *evals, const uint32_t *domain_shifts_monty, size_t n,
+                  unsigned log_blowup, int layout, uint8_t root[32], ts_tree **out) {
+    std::vector<ts_matrix *> ldes;
+    int rc = TS_OK;
+    for (size_t i = 0; i < n && rc == TS_OK; i++) {
+        // shift = Val::generator() / domain.shift   (two_adic_pcs.rs:235)
+        const uint32_t dshift = h_from_monty(domain_shifts_monty[i]);
+        if (dshift == 0) {
+            c->err = "pcs commit: zero domain shift";
+            rc = TS_ERR_ARG;
+            break;
+        }
+        const uint32_t shift = h_to_monty(bb::cmul(31, bb::cinv(dshift)));
+        ts_matrix *lde = nullptr;
+        rc = ts_coset_lde_batch(c, evals[i], log_blowup, shift, 0, &lde);
+        if (rc == TS_OK) ldes.push_back(lde);
+    }
+    if (rc == TS_OK) rc = mmcs_commit(c, ldes.data(), ldes.size(), layout, 1, root, out, true);
+    if (rc != TS_OK)
+        for (ts_matrix *m : ldes) ts_matrix_free(m);
+    return rc;
+}
+int ts_pcs_commit_host(ts_ctx *c, const uint32_t *const *evals_host, const size_t *rows, const size_t *widths,
+                       const uint32_t *domain_shifts_monty, size_t n, unsigned log_blowup, int layout,
+                       uint8_t root[32], ts_tree **out) {
+    std::vector<ts_matrix *> in(n, nullptr);
+    int rc = TS_OK;
+    for (size_t i = 0; i < n && rc == TS_OK; i++) rc = ts_matrix_from_host(c, evals_host[i], rows[i], widths[i], &in[i]);
+    if (rc == TS_OK) rc = ts_pcs_commit(c, in.data(), domain_shifts_monty, n, log_blowup, layout, root, out);
+    for (ts_matrix *m : in) ts_matrix_free(m);
+    return rc;
+}
+int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, size_t domain_size, uint32_t *out_host) {
+    if (idx >= t->mats.size()) TS_FAIL(c, TS_ERR_ARG, "get_evaluations_on_domain: no such matrix");
+    const ts_matrix *lde = t->mats[idx];
+    const int ld = log2_strict(domain_size);
+    if (ld < 0 || domain_size > lde->rows) TS_FAIL(c, TS_ERR_ARG, "get_evaluations_on_domain: bad domain size");
+    ts_matrix *tmp = nullptr;
+    TS_TRY(new_matrix(c, domain_size, lde->width, &tmp));
+    int rc = bitrev_rows(c, lde->d, tmp->d, ld, lde->width);  // split_rows(size).0.bit_reverse_rows()
+    if (rc == TS_OK) rc = ts_matrix_download(c, tmp, 0, domain_size, out_host);
+    ts_matrix_free(tmp);
+    return rc;
+}
+int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out) {
+    std::vector<uint32_t> apow(m->width * 4);
+    uint32_t cur[4] = {1, 0, 0, 0}, a[4];
+    for (int i = 0; i < 4; i++) a[i] = h_from_monty(alpha_monty[i]);
+    for (size_t k = 0; k < m->width; k++) {
+        for (int i = 0; i < 4; i++) apow[4 * k + i] = h_to_monty(cur[i]);
+        uint32_t nx[4];
+        h_ef_mul(cur, a, nx);
+        memcpy(cur, nx, 16);
+    }
+    ts_matrix *ap = nullptr, *o = nullptr;
+    TS_TRY(ts_matrix_from_host(c, apow.data(), m->width, 4, &ap));
+    int rc = new_matrix(c, m->rows, 4, &o);
+    if (rc == TS_OK) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = fold::dot_ext_powers_kernel;
+        TS_LAUNCH(kfn, (unsigned)((m->rows + fold::DOT_ROWS - 1) / fold::DOT_ROWS), 256,
+                  (size_t)fold::DOT_ROWS * (fold::DOT_COLS + 1) * 4, c->stream, (const uint32_t *)m->d, m->rows,
+                  (uint32_t)m->width, (const uint4 *)ap->d, (uint4 *)o->d);
+        rc = check_launch(c, "dot_ext_powers_kernel");
+    }
+    // apow is read by the kernel: free only after the stream has consumed it
+    if (rc == TS_OK) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            c->err = cudaGetErrorString(e);
+            rc = TS_ERR_CUDA;
+        }
+    }
+    ts_matrix_free(ap);
+    if (rc != TS_OK) {
+        ts_matrix_free(o);
+        return rc;
+    }
+    *out = o;
+    return TS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""Parity cases shared by the emulated (no GPU) and the real-GPU test modules.  Every case drives the C ABI
+through the host-side mirror (tap-stark_b200/__init__.py) and compares bit-exactly with the CPU oracle."""
+import numpy as np
+
+P = 0x78000001
+
+
+def rand_mat(seed, rows, width):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, P, (rows, width), dtype=np.uint32)
+
+
+# ---- LDE (fri/src/two_adic_pcs.rs:235-240) -----------------------------------------------------
+def check_lde(ts, ctx, orc, log_n, width, added_bits, shift=31, seed=0):
+    ev = rand_mat(seed, 1 << log_n, width)
+    dft = ts.GpuDft(ctx)
+    got = dft.coset_lde_batch(ts.DeviceMatrix.from_canonical(ctx, ev), added_bits, shift, committed_order=True)
+    want = orc.pcs_lde_committed(ev, added_bits, shift)
+    assert got.rows == want.shape[0] and got.width == width
+    assert np.array_equal(got.to_canonical(), want), f"LDE mismatch log_n={log_n} w={width} b={added_bits}"
+
+
+def check_lde_natural_and_host(ts, ctx, orc, log_n, width, added_bits, seed=1):
+    ev = rand_mat(seed, 1 << log_n, width)
+    dft = ts.GpuDft(ctx)
+    nat = dft.coset_lde_batch(ts.DeviceMatrix.from_canonical(ctx, ev), added_bits, 31)
+    want = orc.coset_lde_batch(ev, added_bits, 31)
+    assert np.array_equal(nat.to_canonical(), want)
+    assert np.array_equal(dft.coset_lde_batch_host(ev, added_bits, 31), want)
+
+
+def check_dft_family(ts, ctx, orc, log_n, width, seed=2):
+    m = rand_mat(seed, 1 << log_n, width)
+    dft = ts.GpuDft(ctx)
+    dm = ts.DeviceMatrix.from_canonical(ctx, m)
+    assert np.array_equal(dft.dft_batch(dm).to_canonical(), orc.dft_batch(m))
+    assert np.array_equal(dft.idft_batch(dm).to_canonical(), orc.idft_batch(m))
+    assert np.array_equal(dft.coset_dft_batch(dm, 31).to_canonical(), orc.coset_dft_batch(m, 31))
+    assert np.array_equal(dft.lde_batch(dm, 1).to_canonical(), orc.coset_lde_batch(m, 1, 1))
+
+
+# ---- MMCS ------------------------------------------------------------------------------------------
+def check_mmcs(ts, ctx, orc, shapes, layout, seed=3, indices=(0, 1)):
+    mats = [rand_mat(seed + i, h, w) for i, (h, w) in enumerate(shapes)]
+    mmcs = ts.Blake3MerkleMmcs(ctx, layout)
+    dms = [ts.DeviceMatrix.from_canonical(ctx, m) for m in mats]
+    root, data = mmcs.commit(dms)
+    ref = orc.mmcs_commit(mats, layout)
+    assert root == ref.root, f"root mismatch shapes={shapes} layout={layout}"
+    assert np.array_equal(data.layer(0), ref.layer(0))
+    hmax = max(h for h, _ in shapes)
+    assert mmcs.get_max_height(data) == hmax
+    for idx in indices:
+        idx = idx % hmax
+        rows, path = mmcs.open_batch(idx, data)
+        rrows, rpath = ref.open_batch(idx)
+        for a, b in zip(rows, rrows):
+            assert np.array_equal(a, b)
+        assert np.array_equal(path, rpath)
+        mmcs.verify_batch([h for h, _ in shapes], rows, idx, path, root)
+        assert ref.verify_batch(idx, rows, path)
+        bad = [r.copy() for r in rows]
+        bad[0][0] = (int(bad[0][0]) + 1) % P
+        try:
+            mmcs.verify_batch([h for h, _ in shapes], bad, idx, path, root)
+            raise AssertionError("tampered opening verified")
+        except ts.TapStarkError:
+            pass
+
+
+# ---- fold (fri/src/two_adic_pcs.rs:116-147, fri/src/fold_even_odd.rs) ------------------------------
+def check_fold_ext(ts, ctx, orc, log_h, seed=4):
+    vals = rand_mat(seed, 2 << log_h, 4)
+    beta = rand_mat(seed + 1, 1, 4)[0]
+    got = ts.fold_even_odd(ctx, vals, beta)
+    assert np.array_equal(got, orc.fold_matrix_ef(vals, beta)), f"fold mismatch log_h={log_h}"
+
+
+def check_fold_base_reference_property(ts, ctx, orc, log_n=10, seed=5):
+    """fri/src/fold_even_odd.rs:65-95 verbatim, on the device path."""
+    n = 1 << log_n
+    coeffs = rand_mat(seed, n, 1)
+    dft = ts.GpuDft(ctx)
+    dev = lambda a: ts.DeviceMatrix.from_canonical(ctx, a)
+    evals = dft.dft_batch(dev(coeffs)).to_canonical()
+    even = dft.dft_batch(dev(coeffs[0::2])).to_canonical()
+    odd = dft.dft_batch(dev(coeffs[1::2])).to_canonical()
+    beta = int(rand_mat(seed + 1, 1, 1)[0, 0])
+    expected = (even.astype(np.uint64) + beta * odd.astype(np.uint64)) % P
+    folded = ts.fold_even_odd(ctx, orc.bit_reverse_rows(evals).reshape(-1), beta)
+    folded = orc.bit_reverse_rows(folded.reshape(-1, 1))
+    assert np.array_equal(folded.astype(np.uint64), expected)
+
+
+# ---- challenger (basic/src/challenger/mod.rs) -------------------------------------------------------
+def check_challenger(ts, golden):
+    ch = ts.BfChallenger(ext=False)
+    ch.observe(b"\x01\x01\x01\x01")
+    assert ch.sample() == golden["challenger"]["ref_golden"]["first"]
+    ch.observe(b"\x01\x01\x01\x01")
+    assert ch.sample() == 1103171332  # script_expr/src/challenger_expr.rs:278-296
+    ch = ts.BfChallenger()
+    outs = iter(golden["challenger"]["outputs"])
+    for op in golden["challenger"]["script"]:
+        if op[0] == "observe_digest":
+            ch.observe(bytes.fromhex(op[1]))
+        elif op[0] == "observe":
+            ch.observe(bytes.fromhex(op[1]))
+        elif op[0] == "sample_ef":
+            assert list(ch.sample_ext()) == next(outs)
+        else:
+            assert ch.sample_base() == next(outs)
+
+
+def check_challenger_grind(ts, orc):
+    a, b = ts.BfChallenger(), orc.BfChallenger()
+    d = bytes(range(32))
+    a.observe(d)
+    b.observe_digest(d)
+    v = a.clone()
+    w = a.grind(8)
+    assert w == b.grind(8)
+    assert v.check_witness(8, w)
+    assert a.sample_bits(10) == b.sample_bits(10)
+
+
+# ---- commit phase (fri/src/prover.rs:93-141) -----------------------------------------------------------
+def check_commit_phase(ts, ctx, orc, log_ns, log_blowup, seed=6):
+    inputs = [orc.pcs_lde_committed(rand_mat(seed + i, 1 << ln, 4), log_blowup) for i, ln in enumerate(log_ns)]
+    cfg = ts.FriConfig(log_blowup, 4, 8, ts.Blake3MerkleMmcs(ctx))
+    res = ts.bf_commit_phase(cfg, [ts.DeviceMatrix.from_canonical(ctx, v) for v in inputs], ts.BfChallenger())
+    ref = orc.fri_commit_phase(inputs, log_blowup, orc.BfChallenger(), want_layers=True)
+    assert ref["ok"]
+    assert res.commits == ref["commits"]
+    assert np.array_equal(res.final_poly, ref["final_poly"])
+    assert len(res.data) == ref["rounds"]
+    # prover data of round r opens the committed layer r (bf_answer_query, prover.rs:69-90)
+    mm = cfg.mmcs
+    for r, pd in enumerate(res.data[:3]):
+        idx = 1 % (ref["layers"][r].shape[0] // 2)
+        rows, path = mm.open_batch(idx, pd)
+        assert np.array_equal(rows[0], ref["layers"][r].reshape(-1, 8)[idx])
+        mm.verify_batch([ref["layers"][r].shape[0] // 2], rows, idx, path, res.commits[r])
+
+
+def check_commit_phase_rejects_high_degree(ts, ctx):
+    bad = rand_mat(9, 64, 4)  # random codeword: not low degree (prover.rs:130-134 assert)
+    cfg = ts.FriConfig(1, 4, 8, ts.Blake3MerkleMmcs(ctx))
+    try:
+        ts.bf_commit_phase(cfg, [ts.DeviceMatrix.from_canonical(ctx, bad)], ts.BfChallenger())
+    except ts.TapStarkError as e:
+        assert "not constant" in str(e)
+    else:
+        raise AssertionError("high-degree input accepted")
+
+
+# ---- PCS commit (fri/src/two_adic_pcs.rs:227-258) ---------------------------------------------------------
+def check_pcs_commit(ts, ctx, orc, shapes, log_blowup, layout=0, seed=7):
+    mmcs = ts.Blake3MerkleMmcs(ctx, layout)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(log_blowup, 2, 8, mmcs))
+    evs = [rand_mat(seed + i, 1 << ln, w) for i, (ln, w) in enumerate(shapes)]
+    doms = [pcs.natural_domain_for_degree(1 << ln) for ln, _ in shapes]
+    root, data = pcs.commit([(d, ts.DeviceMatrix.from_canonical(ctx, e)) for d, e in zip(doms, evs)])
+    ldes = [orc.pcs_lde_committed(e, log_blowup) for e in evs]
+    assert root == orc.mmcs_commit(ldes, layout).root
+    root2, _ = pcs.commit_host([(d, ts.to_monty(e)) for d, e in zip(doms, evs)])
+    assert root2 == root
+    # get_evaluations_on_domain: evaluations on g*H_n, natural order (two_adic_pcs.rs:247-258)
+    ln, _ = shapes[0]
+    got = pcs.get_evaluations_on_domain(data, 0, ts.TwoAdicMultiplicativeCoset(ln, 31))
+    assert np.array_equal(got, orc.coset_dft_batch(orc.idft_batch(evs[0]), 31))
+    # quotient-chunk style domain (uni-stark/src/prover.rs:78-83): domain.shift = 31 => LDE shift 1
+    q = rand_mat(seed + 50, 1 << ln, 4)
+    rootq, _ = pcs.commit([(ts.TwoAdicMultiplicativeCoset(ln, 31), ts.DeviceMatrix.from_canonical(ctx, q))])
+    assert rootq == orc.mmcs_commit([orc.pcs_lde_committed(q, log_blowup, 1)], layout).root
+
+
+def check_dot_ext_powers(ts, ctx, orc, rows, width, seed=8):
+    m = rand_mat(seed, rows, width)
+    alpha = rand_mat(seed + 1, 1, 4)[0]
+    mmcs = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(1, 2, 8, mmcs))
+    got = pcs.dot_ext_powers(ts.DeviceMatrix.from_canonical(ctx, m), alpha).to_canonical()
+    acc = np.zeros((rows, 4), dtype=np.uint64)
+    cur = np.array([1, 0, 0, 0], dtype=np.uint32)
+    for c in range(width):
+        acc = (acc + m[:, c : c + 1].astype(np.uint64) * cur.astype(np.uint64)) % P
+        cur = orc.ef_mul(cur, alpha)
+    assert np.array_equal(got, acc.astype(np.uint32))

@@ -1,0 +1,121 @@
+"""Kernel-source parity WITHOUT a GPU: tap-stark_b200/csrc compiled by g++ against the SIMT emulator in
+tests/emul (test-only; see tests/emul/cuda_emul.h) and compared bit-exactly with the oracle.  These are the
+same cases the GPU module runs on the real library, at emulator-friendly sizes."""
+import pytest
+
+import parity_cases as pc
+
+
+@pytest.fixture(scope="module")
+def ts():
+    from emul.build_emul import build
+
+    from __graft_entry__ import load_pkg
+
+    pkg = load_pkg()
+    pkg.load_library(build(), allow_emulated=True)
+    yield pkg
+    pkg._lib = None
+
+
+@pytest.fixture(scope="module")
+def ctx(ts):
+    c = ts.Context(0)
+    yield c
+    c.close()
+
+
+def test_product_loader_rejects_emulated_library(ts):
+    from emul.build_emul import OUT
+
+    keep = ts._lib
+    with pytest.raises(ts.TapStarkError):
+        ts.load_library(OUT)  # allow_emulated defaults to False: the product path never computes on a CPU
+    ts._lib = keep
+
+
+@pytest.mark.parametrize("log_n,width,b", [(0, 3, 2), (1, 1, 1), (2, 2, 2), (3, 5, 1), (4, 8, 2), (5, 3, 3),
+                                           (7, 2, 2), (9, 9, 1), (10, 2, 2), (11, 8, 2)])
+def test_lde_single_digit(ts, ctx, orc, log_n, width, b):
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+@pytest.mark.parametrize("log_n,width,b", [(12, 3, 1), (13, 8, 2), (14, 1, 2), (12, 17, 2)])
+def test_lde_two_digits(ts, ctx, orc, log_n, width, b):
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+def test_lde_other_shift(ts, ctx, orc):
+    pc.check_lde(ts, ctx, orc, 6, 4, 2, shift=1)
+    pc.check_lde(ts, ctx, orc, 12, 2, 1, shift=pow(31, 5, pc.P))
+
+
+def test_lde_natural_and_host(ts, ctx, orc):
+    pc.check_lde_natural_and_host(ts, ctx, orc, 6, 3, 2)
+
+
+@pytest.mark.parametrize("log_n,width", [(0, 2), (3, 3), (8, 2), (12, 2)])
+def test_dft_family(ts, ctx, orc, log_n, width):
+    pc.check_dft_family(ts, ctx, orc, log_n, width)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("shapes", [[(1, 5)], [(2, 1)], [(64, 8)], [(256, 16)], [(128, 40)], [(8, 300)],
+                                    [(4, 600)], [(32, 3), (32, 7)], [(8, 3), (32, 2), (8, 5), (32, 1), (2, 4)],
+                                    [(16, 8), (4, 8)]])
+def test_mmcs(ts, ctx, orc, shapes, layout):
+    pc.check_mmcs(ts, ctx, orc, shapes, layout, indices=(0, 1, 5, 31))
+
+
+def test_mmcs_fri_leaf_width(ts, ctx, orc):
+    pc.check_mmcs(ts, ctx, orc, [(512, 8)], 0, indices=(0, 300))
+
+
+@pytest.mark.parametrize("log_h", [0, 1, 3, 7, 8, 9, 11])
+def test_fold_ext(ts, ctx, orc, log_h):
+    pc.check_fold_ext(ts, ctx, orc, log_h)
+
+
+def test_fold_golden(ts, ctx, golden):
+    import numpy as np
+
+    for case in golden["fold_ef"]:
+        got = ts.fold_even_odd(ctx, np.array(case["vals"], dtype=np.uint32), case["beta"])
+        assert got.tolist() == case["out"]
+
+
+def test_fold_base_reference_property(ts, ctx, orc):
+    pc.check_fold_base_reference_property(ts, ctx, orc, log_n=8)
+
+
+def test_challenger(ts, orc, golden):
+    pc.check_challenger(ts, golden)
+    pc.check_challenger_grind(ts, orc)
+
+
+def test_commit_phase(ts, ctx, orc):
+    pc.check_commit_phase(ts, ctx, orc, [6], 2)
+    pc.check_commit_phase(ts, ctx, orc, [7, 5, 4], 1)
+    pc.check_commit_phase_rejects_high_degree(ts, ctx)
+
+
+def test_commit_phase_golden(ts, ctx, orc, golden):
+    import numpy as np
+
+    g = golden["commit_phase"]
+    cw = orc.pcs_lde_committed(np.array(g["evals"], dtype=np.uint32), g["log_blowup"])
+    cfg = ts.FriConfig(g["log_blowup"], 4, 8, ts.Blake3MerkleMmcs(ctx))
+    res = ts.bf_commit_phase(cfg, [ts.DeviceMatrix.from_canonical(ctx, cw)], ts.BfChallenger())
+    assert [c.hex() for c in res.commits] == g["commits"]
+    assert res.final_poly.tolist() == g["final_poly"]
+
+
+def test_pcs_commit(ts, ctx, orc):
+    pc.check_pcs_commit(ts, ctx, orc, [(5, 3)], 2)
+    pc.check_pcs_commit(ts, ctx, orc, [(6, 2), (4, 5), (6, 1)], 1)
+    pc.check_pcs_commit(ts, ctx, orc, [(6, 2), (4, 5)], 1, layout=1)
+
+
+def test_dot_ext_powers(ts, ctx, orc):
+    pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
+    pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
