@@ -67,6 +67,9 @@ int ts_ctx_set_profiling(ts_ctx *ctx, int on);
 int ts_ctx_reset_stats(ts_ctx *ctx);
 int ts_ctx_get_stats(ts_ctx *ctx, int kind, double *ms, uint64_t *launches);
 uint64_t ts_ctx_total_launches(const ts_ctx *ctx);
+/* Freed matrices/trees go to a stream-ordered cache instead of cudaFree (which would synchronise the device
+ * every step); ts_ctx_trim returns the cache to the driver. */
+int ts_ctx_trim(ts_ctx *ctx);
 
 /* ---------------------------------------------------------------- matrices */
 int ts_matrix_alloc(ts_ctx *ctx, size_t rows, size_t width, ts_matrix **out);

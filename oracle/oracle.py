@@ -86,6 +86,7 @@ def lib():
         "or_fold_matrix_bb": (None, [u32p, C.c_uint, C.c_uint32, u32p]),
         "or_fold_matrix_ef": (None, [u32p, C.c_uint, u32p, u32p]),
         "or_fold_row_ef": (None, [C.c_size_t, C.c_uint, u32p, u32p, u32p, u32p]),
+        "or_dot_ext_powers": (None, [u32p, C.c_size_t, C.c_size_t, u32p, u32p]),
         "or_chal_init": (None, [C.POINTER(Challenger), C.c_int]),
         "or_chal_observe": (None, [C.POINTER(Challenger), u8p]),
         "or_chal_observe_digest": (None, [C.POINTER(Challenger), u8p]),
@@ -303,6 +304,15 @@ def fold_row_ef(index: int, log_height: int, beta, e0, e1) -> np.ndarray:
     out = np.zeros(4, dtype=np.uint32)
     a = [np.ascontiguousarray(x, dtype=np.uint32) for x in (beta, e0, e1)]
     lib().or_fold_row_ef(index, log_height, _u32p(a[0]), _u32p(a[1]), _u32p(a[2]), _u32p(out))
+    return out
+
+
+def dot_ext_powers(m: np.ndarray, alpha) -> np.ndarray:
+    """fri/src/two_adic_pcs.rs:375: (rows, 4) EF vector sum_c alpha^c * m[:, c]."""
+    m = np.ascontiguousarray(m, dtype=np.uint32)
+    a = np.ascontiguousarray(alpha, dtype=np.uint32)
+    out = np.empty((m.shape[0], 4), dtype=np.uint32)
+    lib().or_dot_ext_powers(_u32p(m.reshape(-1)), m.shape[0], m.shape[1], _u32p(a), _u32p(out.reshape(-1)))
     return out
 
 

@@ -614,6 +614,27 @@ void or_fold_row_ef(size_t index, unsigned log_height, const uint32_t beta[4],
     or_ef_add(e0, t, out);
 }
 
+/* ============================== dot_ext_powers ======================================= */
+/* fri/src/two_adic_pcs.rs:375 `mat.dot_ext_powers(alpha)` ([MEM] p3-matrix): out[r] = sum_c alpha^c * m[r][c] */
+void or_dot_ext_powers(const uint32_t *m, size_t rows, size_t w, const uint32_t alpha[4], uint32_t *out) {
+    uint32_t *apow = (uint32_t *)malloc(w * 16);
+    uint32_t cur[4] = {1, 0, 0, 0};
+    for (size_t c = 0; c < w; c++) {
+        memcpy(apow + 4 * c, cur, 16);
+        or_ef_mul(cur, alpha, cur);
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < rows; r++) {
+        uint64_t acc[4] = {0, 0, 0, 0};
+        for (size_t c = 0; c < w; c++) {
+            const uint64_t v = m[r * w + c];
+            for (int k = 0; k < 4; k++) acc[k] = (acc[k] + v * apow[4 * c + k]) % P;
+        }
+        for (int k = 0; k < 4; k++) out[4 * r + k] = (uint32_t)acc[k];
+    }
+    free(apow);
+}
+
 /* ============================== Challenger =========================================== */
 /* basic/src/challenger/mod.rs:22-49 (Blake3Permutation), :151-174 (duplexing), :183-194 (observe),
  * :261-313 (sample), :341-348 (sample_bits), :95-114 (grind / check_witness);

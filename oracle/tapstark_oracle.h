@@ -92,6 +92,9 @@ void or_fold_matrix_ef(const uint32_t *in, unsigned log_h, const uint32_t beta[4
 void or_fold_row_ef(size_t index, unsigned log_height, const uint32_t beta[4],
                     const uint32_t e0[4], const uint32_t e1[4], uint32_t out[4]);
 
+/* fri/src/two_adic_pcs.rs:375 mat.dot_ext_powers(alpha): out[r] (EF) = sum_c alpha^c * m[r][c] */
+void or_dot_ext_powers(const uint32_t *m, size_t rows, size_t w, const uint32_t alpha[4], uint32_t *out);
+
 /* ---- BfChallenger with Blake3Permutation (basic/src/challenger/mod.rs) ---------------------- */
 typedef struct {
     uint8_t state[16][4];

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "ts_ctx_reset_stats": (C.c_int, [_vp]),
     "ts_ctx_get_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ts_ctx_total_launches": (C.c_uint64, [_vp]),
+    "ts_ctx_trim": (C.c_int, [_vp]),
     "ts_matrix_alloc": (C.c_int, [_vp, C.c_size_t, C.c_size_t, _vpp]),
     "ts_matrix_from_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vpp]),
     "ts_matrix_from_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vpp]),
@@ -192,6 +193,9 @@ class Context:
 
     def total_launches(self) -> int:
         return self._L.ts_ctx_total_launches(self._h)
+
+    def trim(self):
+        self._L.ts_ctx_trim(self._h)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -38,6 +38,10 @@ struct ts_ctx {
     std::map<std::tuple<int, int, int, uint32_t>, std::pair<uint2 *, uint2 *>> coset_tabs;
     uint32_t *scratch = nullptr;
     size_t scratch_words = 0;
+    // stream-ordered caching allocator: freed blocks are reused by later work on the same stream without a
+    // device synchronisation (cudaFree would serialise every step of the pipeline)
+    std::multimap<size_t, void *> pool_free;
+    std::map<void *, size_t> pool_sizes;
     // stats
     bool profiling = false;
     double ms[TS_K_COUNT] = {0};
@@ -119,6 +123,42 @@ int check_launch(ts_ctx *c, const char *what) {
         return TS_ERR_CUDA;
     }
     return TS_OK;
+}
+
+void pool_trim(ts_ctx *c) {
+    if (c->pool_free.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->pool_free) {
+        cudaFree(kv.second);
+        c->pool_sizes.erase(kv.second);
+    }
+    c->pool_free.clear();
+}
+cudaError_t pool_alloc(ts_ctx *c, void **p, size_t bytes) {
+    const size_t sz = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    auto it = c->pool_free.find(sz);
+    if (it != c->pool_free.end()) {
+        *p = it->second;
+        c->pool_free.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, sz);
+    if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        pool_trim(c);
+        e = cudaMalloc(p, sz);
+    }
+    if (e == cudaSuccess) c->pool_sizes[*p] = sz;
+    return e;
+}
+void pool_release(ts_ctx *c, void *p) {
+    if (!p) return;
+    auto it = c->pool_sizes.find(p);
+    if (it == c->pool_sizes.end()) {
+        cudaFree(p);
+        return;
+    }
+    c->pool_free.insert({it->second, p});
 }
 
 int log2_strict(size_t x) {
@@ -350,7 +390,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
 
 int new_matrix(ts_ctx *c, size_t rows, size_t width, ts_matrix **out) {
     ts_matrix *m = new ts_matrix{c, nullptr, rows, width, true};
-    cudaError_t e = cudaMalloc((void **)&m->d, std::max<size_t>(rows * width, 1) * 4);
+    cudaError_t e = pool_alloc(c, (void **)&m->d, std::max<size_t>(rows * width, 1) * 4);
     if (e != cudaSuccess) {
         delete m;
         c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
@@ -493,7 +533,7 @@ int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, 
         t->layer_off.push_back(off);
         off += t->hmax >> l;
     }
-    cudaError_t e = cudaMalloc((void **)&t->digests, off * 32);
+    cudaError_t e = pool_alloc(ctx, (void **)&t->digests, off * 32);
     if (e != cudaSuccess) {
         t->own_mats = false;
         ts_tree_free(t);
@@ -630,6 +670,7 @@ void ts_ctx_destroy(ts_ctx *c) {
     cudaFree(c->tw_big);
     cudaFree(c->fold_tlo);
     cudaFree(c->scratch);
+    pool_trim(c);
     for (auto &kv : c->coset_tabs) {
         cudaFree(kv.second.first);
         cudaFree(kv.second.second);
@@ -682,6 +723,10 @@ int ts_ctx_get_stats(ts_ctx *c, int kind, double *ms, uint64_t *launches) {
     return TS_OK;
 }
 uint64_t ts_ctx_total_launches(const ts_ctx *c) { return c->total_launches; }
+int ts_ctx_trim(ts_ctx *c) {
+    pool_trim(c);
+    return TS_OK;
+}
 
 // ---------------------------------------------------------------- matrices
 int ts_matrix_alloc(ts_ctx *c, size_t rows, size_t width, ts_matrix **out) { return new_matrix(c, rows, width, out); }
@@ -710,10 +755,7 @@ size_t ts_matrix_rows(const ts_matrix *m) { return m->rows; }
 size_t ts_matrix_width(const ts_matrix *m) { return m->width; }
 void ts_matrix_free(ts_matrix *m) {
     if (!m) return;
-    if (m->owned && m->d) {
-        cudaStreamSynchronize(m->ctx->stream);
-        cudaFree(m->d);
-    }
+    if (m->owned && m->d) pool_release(m->ctx, m->d);
     delete m;
 }
 static int monty_convert(ts_ctx *c, ts_matrix *m, int to) {
@@ -834,10 +876,7 @@ int ts_tree_layer(ts_ctx *c, const ts_tree *t, size_t layer, uint8_t *out, size_
 }
 void ts_tree_free(ts_tree *t) {
     if (!t) return;
-    if (t->digests) {
-        cudaStreamSynchronize(t->ctx->stream);
-        cudaFree(t->digests);
-    }
+    if (t->digests) pool_release(t->ctx, t->digests);
     for (ts_matrix *m : t->mats)
         if (t->own_mats) ts_matrix_free(m);
     delete t;
@@ -985,10 +1024,10 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
     int rc = TS_OK;
     if (trees && len > blowup) {
         uint32_t *cl = nullptr;
-        TS_CUDA(c, cudaMalloc((void **)&cl, len * 16));
+        TS_CUDA(c, pool_alloc(c, (void **)&cl, len * 16));
         cudaError_t e = cudaMemcpyAsync(cl, cur, len * 16, cudaMemcpyDeviceToDevice, c->stream);
         if (e != cudaSuccess) {
-            cudaFree(cl);
+            pool_release(c, cl);
             TS_FAIL(c, TS_ERR_CUDA, std::string("clone first input: ") + cudaGetErrorString(e));
         }
         cur = cl;
@@ -1012,7 +1051,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         uint32_t beta[4];
         ts_challenger_sample_ext(chal, beta);  // prover.rs:116
         uint32_t *nf = nullptr;
-        cudaError_t e = cudaMalloc((void **)&nf, h * 16);
+        cudaError_t e = pool_alloc(c, (void **)&nf, h * 16);
         if (e != cudaSuccess) {
             c->err = std::string("cudaMalloc folded: ") + cudaGetErrorString(e);
             rc = TS_ERR_CUDA;
@@ -1023,10 +1062,10 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         }
         cur = nullptr;
         cur_owned = false;
-        if (rc != TS_OK || !trees) ts_tree_free(tree);  // synchronises the stream before freeing the layer
+        if (rc != TS_OK || !trees) ts_tree_free(tree);  // the layer returns to the stream-ordered pool
         else trees[round] = tree;
         if (rc != TS_OK) {
-            if (nf) cudaFree(nf);
+            if (nf) pool_release(c, nf);
             break;
         }
         cur = nf;
@@ -1050,10 +1089,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
                 }
         }
     }
-    if (cur_owned && cur) {
-        cudaStreamSynchronize(c->stream);
-        cudaFree(cur);
-    }
+    if (cur_owned && cur) pool_release(c, cur);
     if (rounds_out) *rounds_out = round;
     return rc;
 }

@@ -1,0 +1,212 @@
+"""Parity on a real B200: the shipped CUDA library, through the C ABI, bit-exact against the CPU oracle on
+seeded inputs at oracle-friendly sizes, against the committed golden vectors, and - at BASELINE.json's
+sizes - through size-independent properties (column-subset LDE, open->verify, transcript replay)."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+P = pc.P
+
+
+@pytest.fixture(scope="module")
+def ts():
+    from __graft_entry__ import build_device, load_pkg
+
+    build_device()
+    pkg = load_pkg()
+    pkg.load_library()  # device build only; raises if missing
+    assert pkg.lib().ts_is_device_build() == 1
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def ctx(ts):
+    c = ts.Context(0)
+    yield c
+    c.close()
+
+
+# ---------------------------------------------------------------- LDE
+@pytest.mark.parametrize("log_n,width,b", [(0, 3, 2), (1, 1, 1), (2, 2, 2), (3, 5, 1), (4, 8, 2), (5, 3, 3), (7, 2, 2),
+                                           (9, 9, 1), (10, 2, 2), (11, 8, 2), (11, 64, 1)])
+def test_lde_single_digit(ts, ctx, orc, log_n, width, b):
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+@pytest.mark.parametrize("log_n,width,b", [(12, 3, 1), (13, 8, 2), (14, 1, 2), (12, 17, 2), (16, 64, 2), (18, 16, 2),
+                                           (20, 4, 2), (22, 2, 1), (21, 3, 2)])
+def test_lde_two_digits(ts, ctx, orc, log_n, width, b):
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+@pytest.mark.parametrize("log_n,width,b", [(23, 1, 1), (24, 2, 1), (23, 4, 2)])
+def test_lde_three_digits(ts, ctx, orc, log_n, width, b):
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+def test_lde_other_shifts(ts, ctx, orc):
+    pc.check_lde(ts, ctx, orc, 6, 4, 2, shift=1)
+    pc.check_lde(ts, ctx, orc, 12, 2, 1, shift=pow(31, 5, P))
+    pc.check_lde(ts, ctx, orc, 15, 5, 2, shift=31 * pow(7, P - 2, P) % P)
+
+
+def test_lde_golden(ts, ctx, golden):
+    dft = ts.GpuDft(ctx)
+    for case in golden["lde"]:
+        ev = np.array(case["evals"], dtype=np.uint32)
+        got = dft.coset_lde_batch(ts.DeviceMatrix.from_canonical(ctx, ev), case["added_bits"], case["shift"],
+                                  committed_order=True)
+        assert got.to_canonical().tolist() == case["committed"]
+
+
+def test_lde_natural_and_host(ts, ctx, orc):
+    pc.check_lde_natural_and_host(ts, ctx, orc, 6, 3, 2)
+    pc.check_lde_natural_and_host(ts, ctx, orc, 14, 5, 2)
+
+
+@pytest.mark.parametrize("log_n,width", [(0, 2), (3, 3), (8, 2), (12, 2), (17, 3)])
+def test_dft_family(ts, ctx, orc, log_n, width):
+    pc.check_dft_family(ts, ctx, orc, log_n, width)
+
+
+def test_lde_config2_shape_column_subset(ts, ctx, orc):
+    """BASELINE config 2 (2^20 x 64, log_blowup 2): the LDE is column-independent, so the oracle LDE of a column
+    subset must equal the same columns of the full device result; plus the low-coset property
+    (fri/src/two_adic_pcs.rs:247-258)."""
+    log_n, w, b = 20, 64, 2
+    ev = orc.splitmix_matrix(0, 1 << log_n, w)
+    dft = ts.GpuDft(ctx)
+    got = dft.coset_lde_batch(ts.DeviceMatrix.from_canonical(ctx, ev), b, 31, committed_order=True).to_canonical()
+    cols = [0, 17, 63]
+    want = orc.pcs_lde_committed(np.ascontiguousarray(ev[:, cols]), b)
+    assert np.array_equal(got[:, cols], want)
+    one = dft.coset_lde_batch(ts.DeviceMatrix.from_canonical(ctx, ev), b, 1, committed_order=True)
+    low = one.to_canonical(0, 1 << log_n)
+    assert np.array_equal(orc.bit_reverse_rows(low), ev)  # shift 1: the low coset is the input itself
+
+
+# ---------------------------------------------------------------- MMCS
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("shapes", [[(1, 5)], [(2, 1)], [(64, 8)], [(256, 16)], [(128, 40)], [(8, 300)], [(4, 600)],
+                                    [(2, 5000)], [(32, 3), (32, 7)], [(8, 3), (32, 2), (8, 5), (32, 1), (2, 4)],
+                                    [(16, 8), (4, 8)], [(1 << 14, 256)], [(1 << 12, 200), (1 << 12, 16)],
+                                    [(1 << 15, 8)], [(1 << 10, 64), (1 << 7, 9), (1 << 10, 1)]])
+def test_mmcs(ts, ctx, orc, shapes, layout):
+    pc.check_mmcs(ts, ctx, orc, shapes, layout, indices=(0, 1, 5, 31, 12345))
+
+
+def test_mmcs_golden(ts, ctx, golden):
+    mm = ts.Blake3MerkleMmcs(ctx)
+    for case in golden["merkle_single"]:
+        root, data = mm.commit([ts.DeviceMatrix.from_canonical(ctx, np.array(case["rows"], dtype=np.uint32))])
+        assert root.hex() == case["root"]
+        assert data.layer(0)[0].tobytes().hex() == case["leaf0"]
+
+
+def test_blake3_reference_kats_on_device(ts, ctx, golden):
+    """scripts/src/hashes/blake3.rs:537-587: 16 (resp. 15) LE u32 ones -> the reference's digests; here as the
+    leaf hash of a one-row matrix."""
+    mm = ts.Blake3MerkleMmcs(ctx)
+    for k, w in zip(golden["blake3"]["kats"], (16, 15)):
+        root, _ = mm.commit([ts.DeviceMatrix.from_canonical(ctx, np.ones((1, w), dtype=np.uint32))])
+        assert root.hex() == k["hash"], k["src"]
+
+
+def test_mmcs_large_open_verify(ts, ctx, orc):
+    """2^20 leaves x 64 columns: root against the oracle, random openings verify on the host."""
+    m = orc.splitmix_matrix(3, 1 << 20, 64)
+    mm = ts.Blake3MerkleMmcs(ctx)
+    root, data = mm.commit([ts.DeviceMatrix.from_canonical(ctx, m)])
+    assert root == orc.mmcs_commit([m]).root
+    rng = np.random.default_rng(0)
+    for idx in rng.integers(0, 1 << 20, 8):
+        rows, path = mm.open_batch(int(idx), data)
+        assert np.array_equal(rows[0], m[idx])
+        mm.verify_batch([1 << 20], rows, int(idx), path, root)
+
+
+# ---------------------------------------------------------------- fold / challenger / commit phase
+@pytest.mark.parametrize("log_h", [0, 1, 3, 7, 8, 9, 11, 16, 20])
+def test_fold_ext(ts, ctx, orc, log_h):
+    pc.check_fold_ext(ts, ctx, orc, log_h)
+
+
+def test_fold_golden(ts, ctx, golden):
+    for case in golden["fold_ef"]:
+        got = ts.fold_even_odd(ctx, np.array(case["vals"], dtype=np.uint32), case["beta"])
+        assert got.tolist() == case["out"]
+
+
+def test_fold_base_reference_property(ts, ctx, orc):
+    pc.check_fold_base_reference_property(ts, ctx, orc, log_n=10)  # fri/src/fold_even_odd.rs:65-95
+    pc.check_fold_base_reference_property(ts, ctx, orc, log_n=16)
+
+
+def test_challenger(ts, orc, golden):
+    pc.check_challenger(ts, golden)
+    pc.check_challenger_grind(ts, orc)
+
+
+def test_commit_phase(ts, ctx, orc):
+    pc.check_commit_phase(ts, ctx, orc, [6], 2)
+    pc.check_commit_phase(ts, ctx, orc, [7, 5, 4], 1)
+    pc.check_commit_phase(ts, ctx, orc, [16, 12], 2)
+    pc.check_commit_phase(ts, ctx, orc, [10], 4)
+    pc.check_commit_phase_rejects_high_degree(ts, ctx)
+
+
+def test_commit_phase_golden(ts, ctx, orc, golden):
+    g = golden["commit_phase"]
+    cw = orc.pcs_lde_committed(np.array(g["evals"], dtype=np.uint32), g["log_blowup"])
+    cfg = ts.FriConfig(g["log_blowup"], 4, 8, ts.Blake3MerkleMmcs(ctx))
+    res = ts.bf_commit_phase(cfg, [ts.DeviceMatrix.from_canonical(ctx, cw)], ts.BfChallenger())
+    assert [c.hex() for c in res.commits] == g["commits"]
+    assert res.final_poly.tolist() == g["final_poly"]
+
+
+def test_commit_phase_2_20(ts, ctx, orc):
+    """FRI sweep point (config 5): codeword 2^20 of BabyBear^4, blowup 4 -> 18 rounds, bit-exact transcript."""
+    pc.check_commit_phase(ts, ctx, orc, [18], 2, seed=40)
+
+
+# ---------------------------------------------------------------- PCS
+def test_pcs_commit(ts, ctx, orc):
+    pc.check_pcs_commit(ts, ctx, orc, [(5, 3)], 2)
+    pc.check_pcs_commit(ts, ctx, orc, [(6, 2), (4, 5), (6, 1)], 1)
+    pc.check_pcs_commit(ts, ctx, orc, [(6, 2), (4, 5)], 1, layout=1)
+    pc.check_pcs_commit(ts, ctx, orc, [(10, 2)], 2)  # config 1 shape: Fibonacci trace 2^10 x 2, log_blowup 2
+    pc.check_pcs_commit(ts, ctx, orc, [(14, 40), (14, 4)], 2)
+
+
+def test_dot_ext_powers(ts, ctx, orc):
+    pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
+    pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
+    pc.check_dot_ext_powers(ts, ctx, orc, 1 << 12, 256)
+
+
+def test_full_pipeline_config1(ts, ctx, orc):
+    """Config 1 shape end to end on the device path: trace 2^10 x 2 -> commit -> alpha-reduction -> FRI commit
+    phase (10 rounds to 4 equal values), every transcript value equal to the oracle's."""
+    log_n, w, b = 10, 2, 2
+    trace = orc.splitmix_matrix(1, 1 << log_n, w)
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(b, 16, 8, mm))
+    ch, rch = ts.BfChallenger(), orc.BfChallenger()
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(1 << log_n), ts.DeviceMatrix.from_canonical(ctx, trace))])
+    lde_ref = orc.pcs_lde_committed(trace, b)
+    assert root == orc.mmcs_commit([lde_ref]).root
+    ch.observe(root)
+    rch.observe_digest(root)
+    alpha = ch.sample()
+    assert np.array_equal(alpha, rch.sample_ef())
+    fri_in = pcs.dot_ext_powers(mm.get_matrices(data)[0], alpha)
+    ref_in = fri_in.to_canonical()
+    res = ts.bf_commit_phase(pcs.fri, [fri_in], ch)
+    ref = orc.fri_commit_phase([ref_in], b, rch)
+    assert len(res.commits) == 10 and res.commits == ref["commits"]
+    assert np.array_equal(res.final_poly, ref["final_poly"])
+    w1, w2 = ch.grind(8), rch.grind(8)
+    assert w1 == w2
+    assert [ch.sample_bits(12) for _ in range(16)] == [rch.sample_bits(12) for _ in range(16)]
