@@ -191,6 +191,26 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *ctx, const ts_tree *t, size_t idx, 
  * TwoAdicFriPcs::open (`mat.dot_ext_powers(alpha)`, two_adic_pcs.rs:375).  alpha Montgomery. */
 int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out);
 
+
+/* ---------------------------------------------------------------- sharded building blocks (one process per GPU)
+ * The path shards as SURVEY 8(e): LDE by columns (no communication), one all-to-all to re-shard by rows,
+ * hashing / alpha-reduction / folding on contiguous row ranges; sub-roots are all-gathered (32 bytes per rank)
+ * and the top log2(G) tree levels are hashed on the host.  Collectives live in the host layer
+ * (tap-stark_b200/parallel.py, torch.distributed NCCL); these entry points are the per-rank pieces. */
+/* LDE written into caller-owned memory (e.g. the send buffer of the all-to-all). */
+int ts_coset_lde_batch_into(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
+                            ts_matrix *out);
+/* acc (+)= sum_c alpha^(first_power + c) * m[:, c]; a row shard whose columns arrive as G blocks calls it once
+ * per block with first_power = block * block_width. */
+int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
+                          ts_matrix *acc, int accumulate);
+/* fold rows [first, first + h_local) of a layer of h_global rows (fold_matrix on a contiguous row range);
+ * addend_dev (may be NULL) is the matching slice of the next FRI input. */
+int ts_fri_fold_ext_shard(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                          const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev);
+/* plain Blake3 on the host: compress the G sub-roots into the root (and what the verifier side uses) */
+void ts_blake3_host(const uint8_t *in, size_t len, uint8_t out[32]);
+
 #ifdef __cplusplus
 }
 #endif

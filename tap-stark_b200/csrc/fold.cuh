@@ -37,29 +37,33 @@ struct ChunkDeltas {
 // EF fold.  in: 2h EF (8 u32 per output row), out: h EF.  addend (optional): the next FRI input of length h
 // (fri/src/prover.rs:124-126), added after folding.  tlo[t] = (w_512^-1)^bitrev8(t) (Montgomery), used when
 // log_h >= 8; smaller layers take the direct power.
+// Row-sharded use (multi-GPU): the launch folds rows [first, first + h_local) of a layer of 2^log_h rows;
+// in/out/addend point at the shard.  first and h_local are multiples of 256 when log_h >= 8.
 __global__ void __launch_bounds__(FOLD_T) fold_ext_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
-                                                          const uint4 *__restrict__ addend, int log_h,
-                                                          ef::E4 half_beta, InvRootPows rp, ChunkDeltas dl,
-                                                          const uint32_t *__restrict__ tlo) {
+                                                          const uint4 *__restrict__ addend, int log_h, size_t first,
+                                                          size_t h_local, ef::E4 half_beta, InvRootPows rp,
+                                                          ChunkDeltas dl, const uint32_t *__restrict__ tlo) {
     const ef::E4Const hb = ef::prepare(half_beta);
-    const size_t h = (size_t)1 << log_h;
+    const size_t h = h_local;
     size_t c0 = 0, c1 = 1;
     uint32_t t_lo = bb::MONTY_ONE, t_hi = bb::MONTY_ONE;
     const bool chunked = log_h >= 8;
+    const size_t chunk_first = first >> 8;
     if (chunked) {
         const size_t chunks = h >> 8, cpb = (chunks + gridDim.x - 1) / gridDim.x;
         c0 = (size_t)blockIdx.x * cpb;
         c1 = c0 + cpb < chunks ? c0 + cpb : chunks;
         if (c0 >= c1) return;
         t_lo = tlo[threadIdx.x];
-        t_hi = pow_from_table(rp, brev_bits((uint32_t)c0, log_h - 8));
+        t_hi = pow_from_table(rp, brev_bits((uint32_t)(c0 + chunk_first), log_h - 8));
     } else if (blockIdx.x > 0) {
         return;
     }
     for (size_t c = c0; c < c1; c++) {
         const size_t i = (c << 8) + threadIdx.x;
         if (i < h) {
-            const uint32_t s = chunked ? bb::mmul(t_lo, t_hi) : pow_from_table(rp, brev_bits((uint32_t)i, log_h));
+            const uint32_t s = chunked ? bb::mmul(t_lo, t_hi)
+                                       : pow_from_table(rp, brev_bits((uint32_t)(i + first), log_h));
             const uint4 a = in[2 * i], b = in[2 * i + 1];
             ef::E4 lo{{a.x, a.y, a.z, a.w}}, hi{{b.x, b.y, b.z, b.w}};
             const ef::E4 sum = ef::half(ef::add(lo, hi));
@@ -71,9 +75,9 @@ __global__ void __launch_bounds__(FOLD_T) fold_ext_kernel(const uint4 *__restric
             }
             out[i] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
         }
-        // trailing ones of c -> which delta moves bitrev(c) to bitrev(c+1)
+        // trailing ones of the global chunk index -> which delta moves bitrev(c) to bitrev(c+1)
         int t = 0;
-        for (size_t cc = c; cc & 1; cc >>= 1) t++;
+        for (size_t cc = c + chunk_first; cc & 1; cc >>= 1) t++;
         t_hi = bb::mmul(t_hi, dl.v[t < 27 ? t : 27]);
     }
 }
@@ -97,7 +101,8 @@ __global__ void __launch_bounds__(FOLD_T) fold_base_kernel(const uint2 *__restri
 constexpr int DOT_ROWS = 64;
 constexpr int DOT_COLS = 64;
 __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__restrict__ m, size_t rows, uint32_t width,
-                                                             const uint4 *__restrict__ apow, uint4 *__restrict__ out) {
+                                                             const uint4 *__restrict__ apow, uint4 *__restrict__ out,
+                                                             int accumulate) {
     TS_DYN_SMEM(uint32_t, sm);  // DOT_ROWS x (DOT_COLS+1) data, then 4 partial sets
     uint32_t *tile = sm;
     const int tid = threadIdx.x;
@@ -132,6 +137,11 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__r
             uint32_t s = red[r * 4 + k];
             for (int pp = 1; pp < 4; pp++) s = bb::add(s, red[(pp * DOT_ROWS + r) * 4 + k]);
             o[k] = s;
+        }
+        if (accumulate) {
+            const uint4 prev = out[row0 + r];
+            o[0] = bb::add(o[0], prev.x); o[1] = bb::add(o[1], prev.y);
+            o[2] = bb::add(o[2], prev.z); o[3] = bb::add(o[3], prev.w);
         }
         out[row0 + r] = make_uint4(o[0], o[1], o[2], o[3]);
     }

@@ -567,7 +567,7 @@ void h_ef_mul(const uint32_t a[4], const uint32_t b[4], uint32_t o[4]) {
 }
 
 int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t *addend, int log_h,
-                    const uint32_t beta_canon[4]) {
+                    const uint32_t beta_canon[4], size_t first = 0, size_t h_local = 0) {
     const uint32_t half = bb::cinv(2);
     ef::E4 hb;
     for (int i = 0; i < 4; i++) hb.c[i] = h_to_monty(bb::cmul(beta_canon[i], half));
@@ -592,13 +592,13 @@ int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t
         }
         dl.v[t] = h_to_monty(v);
     }
-    const size_t h = (size_t)1 << log_h;
+    const size_t h = h_local ? h_local : (size_t)1 << log_h;
     unsigned blocks = 1;
     if (log_h >= 8) blocks = (unsigned)std::min<size_t>(h >> 8, (size_t)c->num_sms * 8);
     KScope ks(c, TS_K_FOLD);
     auto kfn = fold::fold_ext_kernel;
     TS_LAUNCH(kfn, blocks, fold::FOLD_T, 0, c->stream, (const uint4 *)in, (uint4 *)out, (const uint4 *)addend, log_h,
-              hb, rp, dl, (const uint32_t *)c->fold_tlo);
+              first, h, hb, rp, dl, (const uint32_t *)c->fold_tlo);
     return check_launch(c, "fold_ext_kernel");
 }
 
@@ -1139,36 +1139,54 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, si
     ts_matrix_free(tmp);
     return rc;
 }
-int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out) {
+static int dot_ext_powers_impl(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
+                               ts_matrix *o, int accumulate) {
     std::vector<uint32_t> apow(m->width * 4);
-    uint32_t cur[4] = {1, 0, 0, 0}, a[4];
+    uint32_t a[4], cur[4] = {1, 0, 0, 0}, base[4];
     for (int i = 0; i < 4; i++) a[i] = h_from_monty(alpha_monty[i]);
+    memcpy(base, a, 16);
+    for (size_t e = first_power; e; e >>= 1) {  // cur = alpha^first_power
+        uint32_t t[4];
+        if (e & 1) {
+            h_ef_mul(cur, base, t);
+            memcpy(cur, t, 16);
+        }
+        h_ef_mul(base, base, t);
+        memcpy(base, t, 16);
+    }
     for (size_t k = 0; k < m->width; k++) {
         for (int i = 0; i < 4; i++) apow[4 * k + i] = h_to_monty(cur[i]);
         uint32_t nx[4];
         h_ef_mul(cur, a, nx);
         memcpy(cur, nx, 16);
     }
-    ts_matrix *ap = nullptr, *o = nullptr;
+    ts_matrix *ap = nullptr;
     TS_TRY(ts_matrix_from_host(c, apow.data(), m->width, 4, &ap));
-    int rc = new_matrix(c, m->rows, 4, &o);
-    if (rc == TS_OK) {
+    int rc;
+    {
         KScope ks(c, TS_K_MISC);
         auto kfn = fold::dot_ext_powers_kernel;
         TS_LAUNCH(kfn, (unsigned)((m->rows + fold::DOT_ROWS - 1) / fold::DOT_ROWS), 256,
                   (size_t)fold::DOT_ROWS * (fold::DOT_COLS + 1) * 4, c->stream, (const uint32_t *)m->d, m->rows,
-                  (uint32_t)m->width, (const uint4 *)ap->d, (uint4 *)o->d);
+                  (uint32_t)m->width, (const uint4 *)ap->d, (uint4 *)o->d, accumulate);
         rc = check_launch(c, "dot_ext_powers_kernel");
     }
-    // apow is read by the kernel: free only after the stream has consumed it
+    // `apow` (pageable host memory) was consumed by a stream-ordered copy; the device copy returns to the
+    // stream-ordered pool, so no synchronisation is needed here
     if (rc == TS_OK) {
-        cudaError_t e = cudaStreamSynchronize(c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);  // apow is a stack-lifetime host buffer
         if (e != cudaSuccess) {
             c->err = cudaGetErrorString(e);
             rc = TS_ERR_CUDA;
         }
     }
     ts_matrix_free(ap);
+    return rc;
+}
+int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out) {
+    ts_matrix *o = nullptr;
+    TS_TRY(new_matrix(c, m->rows, 4, &o));
+    int rc = dot_ext_powers_impl(c, m, alpha_monty, 0, o, 0);
     if (rc != TS_OK) {
         ts_matrix_free(o);
         return rc;
@@ -1176,5 +1194,29 @@ int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[
     *out = o;
     return TS_OK;
 }
+int ts_dot_ext_powers_acc(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
+                          ts_matrix *acc, int accumulate) {
+    if (acc->rows != m->rows || acc->width != 4) TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_acc: acc must be rows x 4");
+    return dot_ext_powers_impl(c, m, alpha_monty, first_power, acc, accumulate);
+}
+
+// ---------------------------------------------------------------- sharded (multi-GPU) building blocks
+int ts_coset_lde_batch_into(ts_ctx *c, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
+                            ts_matrix *out) {
+    if (out->rows != (evals->rows << added_bits) || out->width != evals->width)
+        TS_FAIL(c, TS_ERR_ARG, "coset_lde_batch_into: out must be (rows<<added_bits) x width");
+    return lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, out->d);
+}
+int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                          const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev) {
+    const int lh = log2_strict(h_global);
+    if (lh < 0 || lh > 26 || first + h_local > h_global) TS_FAIL(c, TS_ERR_ARG, "fold shard: bad range");
+    if (lh >= 8 && ((first | h_local) & 255)) TS_FAIL(c, TS_ERR_ARG, "fold shard: range must be a multiple of 256 rows");
+    if (lh < 8 && (first != 0 || h_local != h_global)) TS_FAIL(c, TS_ERR_ARG, "fold shard: small layers are not sharded");
+    uint32_t beta[4];
+    for (int i = 0; i < 4; i++) beta[i] = h_from_monty(beta_monty[i]);
+    return fold_ext_launch(c, in_dev, out_dev, addend_dev, lh, beta, first, h_local);
+}
+void ts_blake3_host(const uint8_t *in, size_t len, uint8_t out[32]) { hostb3::hash(in, len, out); }
 
 }  // extern "C"

@@ -1,0 +1,198 @@
+"""One-process-per-GPU sharding of the commitment path, over torch.distributed.
+
+    LDE            column-sharded: rank r transforms columns [r*w/G, (r+1)*w/G) of every row; no communication
+                   (columns are independent polynomials, fri/src/two_adic_pcs.rs:237-240 is column-wise).
+    re-shard       ONE all-to-all (NCCL over NVLink): rank s sends rows [r*N/G, (r+1)*N/G) of its LDE columns to
+                   rank r.  Committed order is bit-reversed, so a contiguous row range is one Merkle subtree.
+    hash           rank r hashes its N/G full rows -- the G received column blocks are fed to the leaf kernel as
+                   G segments, no interleave pass -- and builds its subtree; the G sub-roots (32 B each) are
+                   all-gathered and the top log2(G) levels hashed on every host: the root equals the 1-GPU root.
+    alpha-reduce   row-local (ts_dot_ext_powers_acc per column block).
+    FRI            row-sharded: pairs (2i, 2i+1) are adjacent, so folding is local; per round one 32-byte
+                   all-gather; when a shard drops below 256 pairs the layer is all-gathered and the remaining
+                   rounds run replicated (identical transcript on every rank).
+
+The same code runs on CPU tensors with the gloo backend against the emulated library (tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import numpy as np
+
+
+class ShardedProver:
+    def __init__(self, ts, ctx, rank: int, world: int, log_blowup: int, device):
+        import torch
+        import torch.distributed as dist
+
+        if world & (world - 1):
+            raise ts.TapStarkError("world size must be a power of two")
+        self.ts, self.ctx, self.rank, self.world, self.b = ts, ctx, rank, world, log_blowup
+        self.torch, self.dist, self.device = torch, dist, device
+        self.mmcs = ts.Blake3MerkleMmcs(ctx)
+        self.cfg = ts.FriConfig(log_blowup, 16, 8, self.mmcs)
+        self.use_batched_p2p = dist.get_backend() != "nccl"
+
+    # ---- plumbing -------------------------------------------------------------------------------------
+    def _wrap(self, t, rows, width):
+        return self.ts.DeviceMatrix.wrap_device(self.ctx, t.data_ptr(), rows, width, keepalive=t)
+
+    def _sync_lib(self):
+        # library work is enqueued on the ctx stream (= torch's current stream on CUDA); the emulated build
+        # is synchronous
+        pass
+
+    def exchange(self, send: List, recv: List):
+        """all-to-all of equally sized chunks: send[s] -> rank s, recv[s] <- rank s."""
+        dist = self.dist
+        if not self.use_batched_p2p:
+            dist.all_to_all(recv, send)
+            return
+        recv[self.rank].copy_(send[self.rank])
+        ops = []
+        for s in range(self.world):
+            if s == self.rank:
+                continue
+            ops.append(dist.P2POp(dist.isend, send[s], s))
+            ops.append(dist.P2POp(dist.irecv, recv[s], s))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def combine_roots(self, sub_root: bytes) -> bytes:
+        """all-gather the G sub-roots and hash the top log2(G) levels (parent = Blake3(left || right))."""
+        torch, dist = self.torch, self.dist
+        mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(self.device)
+        outs = [torch.empty(32, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        dist.all_gather(outs, mine)
+        layer = [bytes(o.cpu().numpy().tobytes()) for o in outs]
+        L = self.ctx._L
+        while len(layer) > 1:
+            nxt = []
+            for i in range(0, len(layer), 2):
+                buf = layer[i] + layer[i + 1]
+                out = (C.c_uint8 * 32)()
+                L.ts_blake3_host(C.c_char_p(buf), 64, out)
+                nxt.append(bytes(out))
+            layer = nxt
+        return layer[0]
+
+    # ---- the step -------------------------------------------------------------------------------------
+    def commit_and_fri(self, trace_t):
+        """trace_t: torch int32 [n, w/G] -- this rank's columns of the trace (Montgomery-form bits).
+        Returns dict(root, commits, final_poly, rounds); identical on every rank."""
+        ts, ctx, torch, G, r, b = self.ts, self.ctx, self.torch, self.world, self.rank, self.b
+        L = ctx._L
+        n, wl = trace_t.shape
+        N = n << b
+        Nl = N // G
+        ev = self._wrap(trace_t, n, wl)
+        lde_t = torch.empty((N, wl), dtype=torch.int32, device=self.device)
+        lde = self._wrap(lde_t, N, wl)
+        gen = int(ts.to_monty(ts.GENERATOR))
+        ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
+        # re-shard by rows
+        recv_t = torch.empty((G, Nl, wl), dtype=torch.int32, device=self.device)
+        self.exchange(list(lde_t.view(G, Nl, wl).unbind(0)), list(recv_t.unbind(0)))
+        del lde, lde_t
+        blocks = [self._wrap(recv_t[s], Nl, wl) for s in range(G)]
+        sub_root, data = self.mmcs.commit(blocks)
+        root = self.combine_roots(sub_root)
+        ch = ts.BfChallenger()
+        ch.observe(root)
+        alpha = ch.sample()
+        am = ts.to_monty(alpha)
+        fri_t = torch.empty((Nl, 4), dtype=torch.int32, device=self.device)
+        fri = self._wrap(fri_t, Nl, 4)
+        for s in range(G):
+            ctx.check(L.ts_dot_ext_powers_acc(ctx._h, blocks[s]._h, am.ctypes.data_as(C.c_void_p), s * wl, fri._h,
+                                              int(s > 0)), "dot_ext_powers_acc")
+        data.free()
+        commits, final = self._fri_commit_phase(fri_t, N, ch)
+        return {"root": root, "commits": commits, "final_poly": final, "rounds": len(commits)}
+
+    def _fri_commit_phase(self, cur_t, len_g: int, ch):
+        """fri/src/prover.rs:93-141 on a row-sharded codeword (cur_t: this rank's [len_g/G, 4] slice)."""
+        ts, ctx, torch, dist, G, r = self.ts, self.ctx, self.torch, self.dist, self.world, self.rank
+        L = ctx._L
+        commits: List[bytes] = []
+        local = cur_t.shape[0]
+        blowup = 1 << self.b
+        while len_g > blowup:
+            h_g, h_l = len_g // 2, local // 2
+            if h_l >= 256 and h_l * G == h_g:
+                leaves = self._wrap(cur_t, h_l, 8)
+                sub, data = self.mmcs.commit([leaves])
+                root = self.combine_roots(sub)
+                data.free()
+                commits.append(root)
+                ch.observe(root)
+                beta = ts.to_monty(ch.sample())
+                out_t = torch.empty((h_l, 4), dtype=torch.int32, device=self.device)
+                ctx.check(L.ts_fri_fold_ext_shard(ctx._h, C.c_void_p(cur_t.data_ptr()), h_g, r * h_l, h_l,
+                                                  beta.ctypes.data_as(C.c_void_p), None, C.c_void_p(out_t.data_ptr())),
+                          "fri_fold_ext_shard")
+                ctx.synchronize()  # cur_t may be released by torch's allocator on rebinding
+                cur_t, len_g, local = out_t, h_g, h_l
+                continue
+            # small layer: gather it everywhere and finish replicated
+            parts = [torch.empty_like(cur_t) for _ in range(G)]
+            dist.all_gather(parts, cur_t)
+            full_t = torch.cat(parts, dim=0).contiguous()
+            res = ts.bf_commit_phase(self.cfg, [self._wrap(full_t, len_g, 4)], ch, keep_data=False)
+            commits += res.commits
+            return commits, res.final_poly.tolist()
+        # len_g <= blowup without ever gathering (only when the input was already tiny)
+        parts = [torch.empty_like(cur_t) for _ in range(G)]
+        dist.all_gather(parts, cur_t)
+        full = torch.cat(parts, dim=0).cpu().numpy().view(np.uint32)
+        vals = ts.from_monty(full)
+        if not all((vals[i] == vals[0]).all() for i in range(vals.shape[0])):
+            raise ts.TapStarkError("commit phase: final layer is not constant")
+        return commits, vals[0].tolist()
+
+
+class ShardedRunner:
+    """bench.py driver for N > 1 (strong scaling: the 2^log_rows x width trace is split by columns)."""
+
+    def __init__(self, ts, ctx, log_rows, width, log_blowup, rank, world):
+        import torch
+
+        self.ts, self.ctx, self.torch = ts, ctx, torch
+        self.rank, self.world = rank, world
+        if width % world:
+            raise ts.TapStarkError("width must be divisible by the number of GPUs")
+        self.n, self.wl, self.b = 1 << log_rows, width // world, log_blowup
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1234 + rank)
+        self.trace_t = torch.randint(0, ts.P, (self.n, self.wl), dtype=torch.int32, device="cuda", generator=g)
+        self.prover = ShardedProver(ts, ctx, rank, world, log_blowup, dev)
+        self.parallelism = (f"{world} GPUs: LDE column-sharded ({self.wl} cols/GPU), NCCL all-to-all re-shard by rows, "
+                            f"row-sharded Blake3 subtrees + FRI folding, 32-byte sub-root all-gathers")
+        self.h2d_bytes = self.n * self.wl * 4
+        self.d2h_bytes = 32 + 32 * log_rows + 16
+        self.host_t = None
+
+    def step_resident(self):
+        return self.prover.commit_and_fri(self.trace_t)
+
+    def prepare_host(self):
+        t = self.torch.empty((self.n, self.wl), dtype=self.torch.int32, pin_memory=True)
+        t.copy_(self.trace_t)
+        self.torch.cuda.synchronize()
+        self.host_t = t
+        self.dev_in = self.torch.empty_like(self.trace_t)
+
+    def step_e2e(self):
+        self.dev_in.copy_(self.host_t, non_blocking=True)  # this rank's column shard, pinned host -> HBM
+        return self.prover.commit_and_fri(self.dev_in)
+
+    def release_host(self):
+        self.host_t = None
+        self.dev_in = None
+
+    def close(self):
+        self.trace_t = None
+        self.ctx.trim()
