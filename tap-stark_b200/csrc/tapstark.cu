@@ -16,6 +16,7 @@
 #include "hash.cuh"
 #include "host_side.h"
 #include "ntt.cuh"
+#include "ntt_fast.cuh"
 
 // ------------------------------------------------------------------------------------------------ structs
 struct ts_matrix {
@@ -32,6 +33,7 @@ struct ts_ctx {
     std::string err;
     int num_sms = 148;
     uint2 *tw_small = nullptr;
+    uint2 *tw_small_inv = nullptr;
     uint2 *tw_big = nullptr;
     int big_log = 0;
     uint32_t *fold_tlo = nullptr;
@@ -184,9 +186,10 @@ int ensure_scratch(ts_ctx *c, size_t words) {
     return TS_OK;
 }
 
-int gen_twiddles(ts_ctx *c, uint2 *out, int log) {
+int gen_twiddles(ts_ctx *c, uint2 *out, int log, bool inverse = false) {
     ntt::RootPows rp;
     uint32_t r = bb::two_adic_generator(log);
+    if (inverse) r = bb::cinv(r);
     for (int k = 0; k < 28; k++) {
         rp.v[k] = h_to_monty(r);
         r = bb::cmul(r, r);
@@ -228,8 +231,52 @@ Lanes choose_lanes(int d, size_t w, int batch_bits, size_t max_tile_words) {
 constexpr size_t kTileWords = 16384;
 
 // one in-place (or src->dst) DIF digit pass over rows of `bits_total` index bits
+nttf::FastTables fast_tables(ts_ctx *c) {
+    nttf::FastTables t;
+    t.tw_small = c->tw_small;
+    t.tw_small_inv = c->tw_small_inv;
+    t.tw_big = c->tw_big;
+    t.big_log = c->big_log;
+    return t;
+}
+bool fast_shape(int d, size_t w) {
+    static const bool off = getenv("TS_NO_FAST") != nullptr;
+    return !off && d >= 9 && d <= 11 && w >= 8 && (w & 3) == 0;
+}
+template <int D>
+int launch_pass_fast(ts_ctx *c, bool inverse, const nttf::FastPassParams &p, size_t blocks) {
+    const size_t smem = (size_t)16384 * 4;
+    KScope ks(c, TS_K_NTT_PASS);
+    if (inverse) {
+        auto kfn = nttf::ntt_pass_fast_kernel<D, true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, nttf::PASS_NT, smem, c->stream, p);
+    } else {
+        auto kfn = nttf::ntt_pass_fast_kernel<D, false>;
+        TS_LAUNCH(kfn, (unsigned)blocks, nttf::PASS_NT, smem, c->stream, p);
+    }
+    return check_launch(c, "ntt_pass_fast_kernel");
+}
+
 int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, size_t w, int d, int lo_bits,
                 int hi_bits, bool has_scale, uint2 scale) {
+    if (!has_scale && fast_shape(d, w)) {
+        nttf::FastPassParams fp;
+        fp.src = src;
+        fp.dst = dst;
+        fp.width = (uint32_t)w;
+        fp.lo_bits = lo_bits;
+        fp.hi_bits = hi_bits;
+        const size_t K = (size_t)1 << (14 - d);
+        fp.n_col_slices = (uint32_t)((w + K - 1) / K);
+        fp.t = fast_tables(c);
+        fp.tw_shift = lo_bits > 0 ? c->big_log - (lo_bits + d) : 0;
+        const size_t blocks = ((size_t)1 << (hi_bits + lo_bits)) * fp.n_col_slices;
+        switch (d) {
+            case 9: return launch_pass_fast<9>(c, inverse, fp, blocks);
+            case 10: return launch_pass_fast<10>(c, inverse, fp, blocks);
+            default: return launch_pass_fast<11>(c, inverse, fp, blocks);
+        }
+    }
     ntt::PassParams p;
     p.src = src;
     p.dst = dst;
@@ -268,6 +315,18 @@ int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, siz
 std::vector<int> split_digits(int m) {
     std::vector<int> d;
     if (m <= 0) return d;
+    if (const char *env = getenv("TS_DIGITS")) {  // test hook: force a digit split, e.g. "11,9"
+        int sum = 0;
+        for (const char *q = env; *q;) {
+            const int v = (int)strtol(q, (char **)&q, 10);
+            if (v < 1 || v > ntt::MAX_DIGIT) break;
+            d.push_back(v);
+            sum += v;
+            if (*q == ',') q++;
+        }
+        if (sum == m) return d;
+        d.clear();
+    }
     const int D = (m + ntt::MAX_DIGIT - 1) / ntt::MAX_DIGIT;
     for (int i = 0; i < D; i++) d.push_back(m / D + (i < m % D ? 1 : 0));
     return d;
@@ -350,7 +409,34 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         used += dg[i];
     }
     // middle kernel
-    {
+    if (fast_shape(dK, w)) {
+        nttf::FastMidParams fp;
+        fp.src = D > 1 ? c->scratch : src;
+        fp.dst = dst;
+        fp.width = (uint32_t)w;
+        fp.klo_bits = klo;
+        fp.b = (int)b;
+        const size_t K = (size_t)1 << (14 - dK);
+        fp.n_col_slices = (uint32_t)((w + K - 1) / K);
+        fp.t = fast_tables(c);
+        fp.tw_shift = klo > 0 ? c->big_log - m : 0;
+        fp.pre_tab = pre;
+        fp.lane_tab = lane;
+        const size_t blocks = ((size_t)1 << klo) * fp.n_col_slices;
+        const size_t smem = (size_t)2 * 16384 * 4 + K * sizeof(uint2);
+        KScope ks(c, TS_K_LDE_MID);
+        if (dK == 9) {
+            auto kfn = nttf::lde_mid_fast_kernel<9>;
+            TS_LAUNCH(kfn, (unsigned)blocks, nttf::MID_NT, smem, c->stream, fp);
+        } else if (dK == 10) {
+            auto kfn = nttf::lde_mid_fast_kernel<10>;
+            TS_LAUNCH(kfn, (unsigned)blocks, nttf::MID_NT, smem, c->stream, fp);
+        } else {
+            auto kfn = nttf::lde_mid_fast_kernel<11>;
+            TS_LAUNCH(kfn, (unsigned)blocks, nttf::MID_NT, smem, c->stream, fp);
+        }
+        TS_TRY(check_launch(c, "lde_mid_fast_kernel"));
+    } else {
         ntt::MidParams p;
         p.src = D > 1 ? c->scratch : src;
         p.dst = dst;
@@ -640,10 +726,21 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(ntt::ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(ntt::ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(ntt::lde_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
     // small twiddle table w_4096^e and the fold's 256-entry low table, built once
     bool ok = cudaMalloc((void **)&c->tw_small, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
+              cudaMalloc((void **)&c->tw_small_inv, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
               cudaMalloc((void **)&c->fold_tlo, 256 * 4) == cudaSuccess;
     if (ok) ok = gen_twiddles(c, c->tw_small, ntt::SMALL_LOG) == TS_OK;
+    if (ok) ok = gen_twiddles(c, c->tw_small_inv, ntt::SMALL_LOG, true) == TS_OK;
     if (ok) {
         uint32_t tlo[256];
         const uint32_t w512inv = bb::cinv(bb::two_adic_generator(9));
@@ -667,6 +764,7 @@ void ts_ctx_destroy(ts_ctx *c) {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
     cudaFree(c->tw_small);
+    cudaFree(c->tw_small_inv);
     cudaFree(c->tw_big);
     cudaFree(c->fold_tlo);
     cudaFree(c->scratch);

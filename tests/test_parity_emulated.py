@@ -45,6 +45,16 @@ def test_lde_two_digits(ts, ctx, orc, log_n, width, b):
     pc.check_lde(ts, ctx, orc, log_n, width, b)
 
 
+@pytest.mark.parametrize("log_n,width,b,digits", [(18, 8, 1, None), (18, 12, 2, None), (19, 8, 1, None),
+                                                  (20, 8, 1, "11,9"), (20, 8, 1, "9,11")])
+def test_lde_fast_path(ts, ctx, orc, log_n, width, b, digits, monkeypatch):
+    """ntt_fast.cuh kernels (digits 9..11, width % 4 == 0); TS_DIGITS forces the split so that D = 11 is
+    reachable at emulator-friendly sizes."""
+    if digits:
+        monkeypatch.setenv("TS_DIGITS", digits)
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
 def test_lde_other_shift(ts, ctx, orc):
     pc.check_lde(ts, ctx, orc, 6, 4, 2, shift=1)
     pc.check_lde(ts, ctx, orc, 12, 2, 1, shift=pow(31, 5, pc.P))
