@@ -147,4 +147,66 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__r
     }
 }
 
+// Hot path of dot_ext_powers for matrices with width % 4 == 0 (the committed LDE): a warp owns 32 rows; per block
+// of 16 columns the lanes issue 4 coalesced LDG.128 each (one block ahead), transpose through a warp-private
+// XOR-swizzled 2 KiB buffer, and every lane accumulates its own row: products are summed in 64 bits in PAIRS
+// (2 p^2 < p 2^32 keeps the Montgomery reduction in range), so one reduction serves two columns.
+// apow must be padded with zeros to a multiple of 16 entries.
+constexpr int DOT_FAST_WARPS = 8;
+__global__ void __launch_bounds__(DOT_FAST_WARPS * 32) dot_rows_fast_kernel(const uint32_t *__restrict__ m, size_t rows,
+                                                                          uint32_t width, const uint4 *__restrict__ apow,
+                                                                          uint4 *__restrict__ out, int accumulate) {
+    TS_DYN_SMEM(uint32_t, sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *ws = sm + warp * 512;
+    const size_t row0 = ((size_t)blockIdx.x * DOT_FAST_WARPS + warp) * 32;
+    if (row0 >= rows) return;  // warp-uniform
+    const uint32_t total_blocks = (width + 15u) / 16u;
+    const uint32_t sub = lane & 3, r0 = lane >> 2;
+    uint4 pf[4];
+    uint32_t acc[4] = {0, 0, 0, 0};
+#define TS_DOT_FETCH(blk_)                                                                           \
+    TS_UNROLL                                                                                        \
+    for (int k = 0; k < 4; k++) {                                                                    \
+        const uint32_t row = r0 + 8 * k, cw = 16u * (blk_) + 4u * sub;                               \
+        pf[k] = (row0 + row < rows && cw < width)                                                    \
+                    ? *reinterpret_cast<const uint4 *>(m + (row0 + row) * width + cw)                \
+                    : make_uint4(0, 0, 0, 0);                                                        \
+    }
+    TS_DOT_FETCH(0u)
+    for (uint32_t blk = 0; blk < total_blocks; blk++) {
+        TS_UNROLL
+        for (int k = 0; k < 4; k++) {
+            const uint32_t row = r0 + 8 * k;
+            *reinterpret_cast<uint4 *>(ws + row * 16 + 4 * (sub ^ ((row >> 1) & 3u))) = pf[k];
+        }
+        __syncwarp();
+        if (blk + 1 < total_blocks) { TS_DOT_FETCH(blk + 1) }
+        uint32_t v[16];
+        TS_UNROLL
+        for (int j = 0; j < 4; j++) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(ws + lane * 16 + 4 * ((uint32_t)j ^ ((lane >> 1) & 3u)));
+            v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+        __syncwarp();
+        TS_UNROLL
+        for (int i = 0; i < 16; i += 2) {
+            const uint4 a0 = __ldg(apow + 16 * blk + i), a1 = __ldg(apow + 16 * blk + i + 1);
+            acc[0] = bb::add(acc[0], bb::redc((uint64_t)v[i] * a0.x + (uint64_t)v[i + 1] * a1.x));
+            acc[1] = bb::add(acc[1], bb::redc((uint64_t)v[i] * a0.y + (uint64_t)v[i + 1] * a1.y));
+            acc[2] = bb::add(acc[2], bb::redc((uint64_t)v[i] * a0.z + (uint64_t)v[i + 1] * a1.z));
+            acc[3] = bb::add(acc[3], bb::redc((uint64_t)v[i] * a0.w + (uint64_t)v[i + 1] * a1.w));
+        }
+    }
+#undef TS_DOT_FETCH
+    if (row0 + lane < rows) {
+        if (accumulate) {
+            const uint4 prev = out[row0 + lane];
+            acc[0] = bb::add(acc[0], prev.x); acc[1] = bb::add(acc[1], prev.y);
+            acc[2] = bb::add(acc[2], prev.z); acc[3] = bb::add(acc[3], prev.w);
+        }
+        out[row0 + lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
 }  // namespace fold

@@ -174,6 +174,100 @@ __global__ void __launch_bounds__(LEAVES_PER_CTA) hash_leaves_kernel(Segments sg
     }
 }
 
+// Per-block state machine shared by the leaf kernels: absorb message block `blk` (0-based) of a leaf of
+// total_words u32 words.  After the last block, cv holds the Blake3 digest.
+TS_D void absorb_block(uint32_t (&cv)[8], uint32_t (*stack)[8], int &sp, const uint32_t (&m)[16], uint32_t blk,
+                       uint32_t total_blocks, uint32_t total_words) {
+    const uint32_t in_chunk = blk & 15u, chunk = blk >> 4;
+    const bool last = (blk + 1 == total_blocks);
+    uint32_t flags = (in_chunk == 0 ? CHUNK_START : 0u) | ((in_chunk == 15 || last) ? CHUNK_END : 0u);
+    const uint32_t rem = total_words - blk * 16u;
+    const uint32_t block_len = total_words == 0 ? 0u : (rem >= 16u ? 64u : rem * 4u);
+    if (last && sp == 0) flags |= ROOT;
+    compress(cv, m, chunk, block_len, flags);
+    if (last) {
+        while (sp > 0) {
+            uint32_t out[8];
+            sp--;
+            compress_pair(stack[sp], cv, PARENT | (sp == 0 ? ROOT : 0u), out);
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) cv[i] = out[i];
+        }
+    } else if (in_chunk == 15) {
+        uint32_t total_chunks = chunk + 1;
+        while ((total_chunks & 1u) == 0) {
+            uint32_t out[8];
+            sp--;
+            compress_pair(stack[sp], cv, PARENT, out);
+            TS_UNROLL
+            for (int i = 0; i < 8; i++) cv[i] = out[i];
+            total_chunks >>= 1;
+        }
+        TS_UNROLL
+        for (int i = 0; i < 8; i++) stack[sp][i] = cv[i];
+        sp++;
+        b3::iv(cv);
+    }
+}
+
+// Hot path: ONE matrix, one row per leaf, width % 4 == 0 (the committed LDE).  A warp owns 32 consecutive
+// leaves.  Per 64-byte block: 4 coalesced LDG.128 per lane (8 rows x 64 B per instruction) are issued one block
+// AHEAD and stay in flight during the compression; the words are converted Montgomery -> canonical once,
+// transposed through a warp-private, XOR-swizzled 2 KiB shared buffer (conflict-free STS.128 and LDS.128), and
+// each lane compresses its own row in registers.  No block-wide barrier.
+constexpr int FAST_WARPS = 8;
+__global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(const uint32_t *__restrict__ rows, uint32_t width,
+                                                                        size_t n_leaves, int monty, uint32_t *digests) {
+    TS_DYN_SMEM(uint32_t, sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *ws = sm + warp * 512;
+    const size_t leaf0 = ((size_t)blockIdx.x * FAST_WARPS + warp) * 32;
+    if (leaf0 >= n_leaves) return;  // warp-uniform
+    const uint32_t total_blocks = (width + 15u) / 16u;
+    const uint32_t sub = lane & 3, r0 = lane >> 2;
+    uint4 pf[4];
+    uint32_t cv[8], stack[MAX_STACK][8];
+    int sp = 0;
+    iv(cv);
+#define TS_FETCH(blk_)                                                                                        \
+    TS_UNROLL                                                                                                 \
+    for (int k = 0; k < 4; k++) {                                                                             \
+        const uint32_t row = r0 + 8 * k, cw = 16u * (blk_) + 4u * sub;                                        \
+        pf[k] = (leaf0 + row < n_leaves && cw < width)                                                        \
+                    ? *reinterpret_cast<const uint4 *>(rows + (leaf0 + row) * width + cw)                     \
+                    : make_uint4(0, 0, 0, 0);                                                                 \
+    }
+    TS_FETCH(0u)
+    for (uint32_t blk = 0; blk < total_blocks; blk++) {
+        TS_UNROLL
+        for (int k = 0; k < 4; k++) {
+            const uint32_t row = r0 + 8 * k;
+            uint4 v = pf[k];
+            if (monty) {
+                v.x = bb::from_monty(v.x); v.y = bb::from_monty(v.y);
+                v.z = bb::from_monty(v.z); v.w = bb::from_monty(v.w);
+            }
+            *reinterpret_cast<uint4 *>(ws + row * 16 + 4 * (sub ^ ((row >> 1) & 3u))) = v;
+        }
+        __syncwarp();
+        if (blk + 1 < total_blocks) { TS_FETCH(blk + 1) }
+        uint32_t m[16];
+        TS_UNROLL
+        for (int j = 0; j < 4; j++) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(ws + lane * 16 + 4 * ((uint32_t)j ^ ((lane >> 1) & 3u)));
+            m[4 * j + 0] = t.x; m[4 * j + 1] = t.y; m[4 * j + 2] = t.z; m[4 * j + 3] = t.w;
+        }
+        __syncwarp();
+        absorb_block(cv, stack, sp, m, blk, total_blocks, width);
+    }
+#undef TS_FETCH
+    if (leaf0 + lane < n_leaves) {
+        uint4 *o = reinterpret_cast<uint4 *>(digests + (leaf0 + lane) * 8);
+        o[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        o[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    }
+}
+
 // Fast path for narrow single-segment leaves (<= 16 words, e.g. the FRI layers: 2 ext elements = 8 words):
 // one thread reads its own contiguous leaf, one compression.
 __global__ void __launch_bounds__(256) hash_leaves_small_kernel(const uint32_t *rows, uint32_t width, size_t n_leaves,

@@ -20,15 +20,18 @@ using ntt::dft_regs;
 using ntt::SMALL_LOG;
 
 struct FastTables {
-    const uint2 *tw_small;      // w_4096^e
-    const uint2 *tw_small_inv;  // w_4096^-e
+    const uint2 *tw_small;      // w_{2^small_log}^e   (global: 4096 entries; lde_mid: a shared-memory copy of 2^D)
+    const uint2 *tw_small_inv;  // w_{2^small_log}^-e
     const uint2 *tw_big;        // w_{2^big_log}^e
     int big_log;
+    int small_log;
 };
 
-template <bool INV>
+// SM: the small tables live in shared memory (plain loads -> LDS); otherwise read-only global loads
+template <bool INV, bool SM>
 TS_D uint2 stw(const FastTables &t, uint32_t e) {
-    return __ldg((INV ? t.tw_small_inv : t.tw_small) + e);
+    const uint2 *p = (INV ? t.tw_small_inv : t.tw_small) + e;
+    return SM ? *p : __ldg(p);
 }
 template <bool INV>
 TS_D uint2 btw(const FastTables &t, uint32_t e) {
@@ -44,18 +47,14 @@ TS_D uint32_t phys(uint32_t lane, uint32_t p) {
 // ---- DIF rounds ----------------------------------------------------------------------------------------
 // M8: radix R = 2^(D-8), elements p = g + 256 c, g = tid & 255.  Optional prescale (lde_mid first round):
 // element c of every lane is multiplied by pos[c] and by the lane scalar.
-template <int D, bool INV, bool PRE, int NT>
-TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const uint2 *pos_tab, const uint2 *lane_w,
+template <int D, bool INV, bool PRE, int NT, bool SM>
+TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const uint2 *pw, const uint2 *lane_w,
                  int tid) {
     constexpr int LOGR = D - 8, R = 1 << LOGR, K = 1 << (14 - D);
     const uint32_t g = tid & 255, sg = g ^ (g >> 4);
-    uint2 tw[R], pw[R];
+    uint2 tw[R];
     TS_UNROLL
-    for (int i = 1; i < R; i++) tw[i] = stw<INV>(t, (g * (uint32_t)brev_c(i, LOGR)) << (SMALL_LOG - D));
-    if (PRE) {
-        TS_UNROLL
-        for (int c = 0; c < R; c++) pw[c] = __ldg(pos_tab + g + 256 * c);
-    }
+    for (int i = 1; i < R; i++) tw[i] = stw<INV, SM>(t, (g * (uint32_t)brev_c(i, LOGR)) << (t.small_log - D));
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sg ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t x[R];
@@ -74,14 +73,14 @@ TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const 
     }
 }
 // M4: radix 16 inside blocks of 256: p = 256 blk + g + 16 c
-template <int D, bool INV, int NT>
+template <int D, bool INV, int NT, bool SM>
 TS_D void dif_m4(uint32_t *tile, const FastTables &t, int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t grp = tid & (G - 1), blk = grp >> 4, g = grp & 15;
     const uint32_t pb = (blk << 8) | ((blk & 1u) << 4) | g;
     uint2 tw[16];
     TS_UNROLL
-    for (int i = 1; i < 16; i++) tw[i] = stw<INV>(t, (g * (uint32_t)brev_c(i, 4)) << (SMALL_LOG - 8));
+    for (int i = 1; i < 16; i++) tw[i] = stw<INV, SM>(t, (g * (uint32_t)brev_c(i, 4)) << (t.small_log - 8));
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t x[16];
@@ -96,16 +95,18 @@ TS_D void dif_m4(uint32_t *tile, const FastTables &t, int tid) {
 }
 // M0: radix 16 on 16 consecutive positions p = 16 g' + i.  POST: multiply position q by the inter-digit
 // twiddle w_{n'}^(+-lo*brev_D(q)) (index pre-shifted by the caller: e = (lo * brev) << tw_shift).
+// the 16 inter-digit twiddles of this thread's M0 group (positions 16 gq + i)
+template <int D, bool INV>
+TS_D void load_post_tw(uint2 (&pt)[16], const FastTables &t, uint32_t lo, int tw_shift, int tid) {
+    const uint32_t gq = tid & ((1 << (D - 4)) - 1);
+    TS_UNROLL
+    for (int i = 0; i < 16; i++) pt[i] = btw<INV>(t, (lo * brev_bits(16u * gq + i, D)) << tw_shift);
+}
 template <int D, bool INV, bool POST, int NT>
-TS_D void dif_m0(uint32_t *tile, const FastTables &t, uint32_t lo, int tw_shift, int tid) {
+TS_D void dif_m0(uint32_t *tile, const uint2 (&pt)[16], int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t gq = tid & (G - 1);
     const uint32_t pb = (gq << 4) ^ (gq & 15u) ^ (((gq >> 4) & 1u) << 4);
-    uint2 pt[16];
-    if (POST) {
-        TS_UNROLL
-        for (int i = 0; i < 16; i++) pt[i] = btw<INV>(t, (lo * brev_bits(16u * gq + i, D)) << tw_shift);
-    }
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t x[16];
@@ -137,14 +138,14 @@ TS_D void dit_m0(uint32_t *tile, int tid) {
         for (int u = 0; u < 16; u++) tile[base ^ (uint32_t)u] = v[brev_c(u, 4)];
     }
 }
-template <int D, int NT>
+template <int D, int NT, bool SM>
 TS_D void dit_m4(uint32_t *tile, const FastTables &t, int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t grp = tid & (G - 1), blk = grp >> 4, j = grp & 15;
     const uint32_t pb = (blk << 8) | ((blk & 1u) << 4) | j;
     uint2 tw[16];  // for digit c: w_256^-(c j)
     TS_UNROLL
-    for (int c = 1; c < 16; c++) tw[c] = stw<true>(t, ((uint32_t)c * j) << (SMALL_LOG - 8));
+    for (int c = 1; c < 16; c++) tw[c] = stw<true, SM>(t, ((uint32_t)c * j) << (t.small_log - 8));
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t v[16];
@@ -157,13 +158,13 @@ TS_D void dit_m4(uint32_t *tile, const FastTables &t, int tid) {
         for (int u = 0; u < 16; u++) tile[base ^ (17u * u)] = v[brev_c(u, 4)];
     }
 }
-template <int D, int NT>
+template <int D, int NT, bool SM>
 TS_D void dit_m8(uint32_t *tile, const FastTables &t, int tid) {
     constexpr int LOGR = D - 8, R = 1 << LOGR, K = 1 << (14 - D);
     const uint32_t j = tid & 255, sj = j ^ (j >> 4);
     uint2 tw[R];
     TS_UNROLL
-    for (int c = 1; c < R; c++) tw[c] = stw<true>(t, ((uint32_t)c * j) << (SMALL_LOG - D));
+    for (int c = 1; c < R; c++) tw[c] = stw<true, SM>(t, ((uint32_t)c * j) << (t.small_log - D));
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sj ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t v[R];
@@ -255,12 +256,14 @@ __global__ void __launch_bounds__(PASS_NT, 3) ntt_pass_fast_kernel(FastPassParam
     const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo, row_stride = (size_t)1 << p.lo_bits;
     load_tile<D, false, PASS_NT>(tile, p.src, row_base, row_stride, p.width, col0, tid);
     __syncthreads();
-    dif_m8<D, INV, false, PASS_NT>(tile, tile, p.t, nullptr, nullptr, tid);
+    dif_m8<D, INV, false, PASS_NT, false>(tile, tile, p.t, nullptr, nullptr, tid);
     __syncthreads();
-    dif_m4<D, INV, PASS_NT>(tile, p.t, tid);
+    dif_m4<D, INV, PASS_NT, false>(tile, p.t, tid);
+    uint2 pt[16];  // 3 CTAs per SM overlap this fetch; holding it across rounds would spill at 80 registers
+    if (p.lo_bits > 0) load_post_tw<D, INV>(pt, p.t, lo, p.tw_shift, tid);
     __syncthreads();
-    if (p.lo_bits > 0) dif_m0<D, INV, true, PASS_NT>(tile, p.t, lo, p.tw_shift, tid);
-    else dif_m0<D, INV, false, PASS_NT>(tile, p.t, 0, 0, tid);
+    if (p.lo_bits > 0) dif_m0<D, INV, true, PASS_NT>(tile, pt, tid);
+    else dif_m0<D, INV, false, PASS_NT>(tile, pt, tid);
     __syncthreads();
     store_tile<D, PASS_NT>(tile, p.dst, row_base, row_stride, p.width, col0, tid);
 }
@@ -281,30 +284,58 @@ constexpr int MID_NT = 512;
 template <int D>
 __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p) {
     TS_DYN_SMEM(uint32_t, smem);
-    constexpr int L = 1 << D, K = 1 << (14 - D);
+    constexpr int L = 1 << D, K = 1 << (14 - D), R8 = 1 << (D - 8);
     uint32_t *A = smem, *W = smem + K * L;
-    uint2 *lane_w = reinterpret_cast<uint2 *>(W + K * L);
+    uint2 *twf = reinterpret_cast<uint2 *>(W + K * L);  // shared copies of w_{2^D}^(+-e): twiddle reads become LDS
+    uint2 *twi = twf + L;
+    uint2 *lane_w = twi + L;
     const int tid = threadIdx.x;
     const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = blockIdx.x / p.n_col_slices;
     const uint32_t col0 = cs << (14 - D);
     const int m = D + p.klo_bits;
+    // inter-digit twiddles w_n^(Kc * brev(q)) do not depend on the coset: fetched once, in flight during the
+    // whole inverse sub-transform
+    uint2 pt[16];
+    if (p.klo_bits > 0) load_post_tw<D, false>(pt, p.t, Kc, p.tw_shift, tid);
+    for (int i = tid; i < L; i += MID_NT) {
+        twf[i] = __ldg(p.t.tw_small + ((size_t)i << (p.t.small_log - D)));
+        twi[i] = __ldg(p.t.tw_small_inv + ((size_t)i << (p.t.small_log - D)));
+    }
+    FastTables ts = p.t;
+    ts.tw_small = twf;
+    ts.tw_small_inv = twi;
+    ts.small_log = D;
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
     load_tile<D, true, MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.width, col0, tid);
     __syncthreads();
     dit_m0<D, MID_NT>(A, tid);
     __syncthreads();
-    dit_m4<D, MID_NT>(A, p.t, tid);
+    dit_m4<D, MID_NT, true>(A, ts, tid);
     __syncthreads();
-    dit_m8<D, MID_NT>(A, p.t, tid);
+    // coset prescale factors of this thread's first-round elements (k_hi = g + 256 c), fetched one coset ahead
+    uint2 pw[R8], pw_next[R8];
+    {
+        const uint32_t g = tid & 255;
+        TS_UNROLL
+        for (int c = 0; c < R8; c++) pw_next[c] = __ldg(p.pre_tab + g + 256 * c);
+    }
+    dit_m8<D, MID_NT, true>(A, ts, tid);
     for (uint32_t j = 0; j < (1u << p.b); j++) {
         if (tid < K) lane_w[tid] = p.lane_tab[((size_t)j << p.klo_bits) + Kc];
+        TS_UNROLL
+        for (int c = 0; c < R8; c++) pw[c] = pw_next[c];
+        if (j + 1 < (1u << p.b)) {
+            const uint32_t g = tid & 255;
+            TS_UNROLL
+            for (int c = 0; c < R8; c++) pw_next[c] = __ldg(p.pre_tab + ((size_t)(j + 1) << D) + g + 256 * c);
+        }
         __syncthreads();  // also orders the last DIT round / the previous coset's store before W is rewritten
-        dif_m8<D, false, true, MID_NT>(A, W, p.t, p.pre_tab + ((size_t)j << D), lane_w, tid);
+        dif_m8<D, false, true, MID_NT, true>(A, W, ts, pw, lane_w, tid);
         __syncthreads();
-        dif_m4<D, false, MID_NT>(W, p.t, tid);
+        dif_m4<D, false, MID_NT, true>(W, ts, tid);
         __syncthreads();
-        if (p.klo_bits > 0) dif_m0<D, false, true, MID_NT>(W, p.t, Kc, p.tw_shift, tid);
-        else dif_m0<D, false, false, MID_NT>(W, p.t, 0, 0, tid);
+        if (p.klo_bits > 0) dif_m0<D, false, true, MID_NT>(W, pt, tid);
+        else dif_m0<D, false, false, MID_NT>(W, pt, tid);
         __syncthreads();
         store_tile<D, MID_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.width, col0, tid);
     }

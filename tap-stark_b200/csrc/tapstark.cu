@@ -237,6 +237,7 @@ nttf::FastTables fast_tables(ts_ctx *c) {
     t.tw_small_inv = c->tw_small_inv;
     t.tw_big = c->tw_big;
     t.big_log = c->big_log;
+    t.small_log = ntt::SMALL_LOG;
     return t;
 }
 bool fast_shape(int d, size_t w) {
@@ -423,7 +424,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         fp.pre_tab = pre;
         fp.lane_tab = lane;
         const size_t blocks = ((size_t)1 << klo) * fp.n_col_slices;
-        const size_t smem = (size_t)2 * 16384 * 4 + K * sizeof(uint2);
+        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + K) * sizeof(uint2);
         KScope ks(c, TS_K_LDE_MID);
         if (dK == 9) {
             auto kfn = nttf::lde_mid_fast_kernel<9>;
@@ -505,6 +506,16 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
         TS_LAUNCH(kfn, (unsigned)((n_leaves + 255) / 256), 256, 0, c->stream, (const uint32_t *)mats[0]->d,
                   (uint32_t)mats[0]->width, n_leaves, 1, digests);
         return check_launch(c, "hash_leaves_small_kernel");
+    }
+    if (mats.size() == 1 && shifts[0] == 0 && (mats[0]->width & 3) == 0 && mats[0]->width <= (256u << b3::MAX_STACK) &&
+        getenv("TS_NO_FAST") == nullptr) {
+        KScope ks(c, TS_K_HASH_LEAVES);
+        auto kfn = b3::hash_rows_fast_kernel;
+        const size_t per_block = (size_t)b3::FAST_WARPS * 32;
+        TS_LAUNCH(kfn, (unsigned)((n_leaves + per_block - 1) / per_block), b3::FAST_WARPS * 32,
+                  (size_t)b3::FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)mats[0]->d, (uint32_t)mats[0]->width,
+                  n_leaves, 1, digests);
+        return check_launch(c, "hash_rows_fast_kernel");
     }
     b3::Segments sg;
     sg.n = (int)mats.size();
@@ -732,9 +743,9 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
     // small twiddle table w_4096^e and the fold's 256-entry low table, built once
     bool ok = cudaMalloc((void **)&c->tw_small, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
               cudaMalloc((void **)&c->tw_small_inv, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
@@ -1239,7 +1250,8 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, si
 }
 static int dot_ext_powers_impl(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
                                ts_matrix *o, int accumulate) {
-    std::vector<uint32_t> apow(m->width * 4);
+    const size_t wpad = (m->width + 15) & ~(size_t)15;  // zero padding: the fast kernel reads whole 16-column blocks
+    std::vector<uint32_t> apow(wpad * 4, 0u);
     uint32_t a[4], cur[4] = {1, 0, 0, 0}, base[4];
     for (int i = 0; i < 4; i++) a[i] = h_from_monty(alpha_monty[i]);
     memcpy(base, a, 16);
@@ -1259,9 +1271,17 @@ static int dot_ext_powers_impl(ts_ctx *c, const ts_matrix *m, const uint32_t alp
         memcpy(cur, nx, 16);
     }
     ts_matrix *ap = nullptr;
-    TS_TRY(ts_matrix_from_host(c, apow.data(), m->width, 4, &ap));
+    TS_TRY(ts_matrix_from_host(c, apow.data(), wpad, 4, &ap));
     int rc;
-    {
+    if ((m->width & 3) == 0 && getenv("TS_NO_FAST") == nullptr) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = fold::dot_rows_fast_kernel;
+        const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
+        TS_LAUNCH(kfn, (unsigned)((m->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
+                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)m->d, m->rows, (uint32_t)m->width,
+                  (const uint4 *)ap->d, (uint4 *)o->d, accumulate);
+        rc = check_launch(c, "dot_rows_fast_kernel");
+    } else {
         KScope ks(c, TS_K_MISC);
         auto kfn = fold::dot_ext_powers_kernel;
         TS_LAUNCH(kfn, (unsigned)((m->rows + fold::DOT_ROWS - 1) / fold::DOT_ROWS), 256,

@@ -45,6 +45,9 @@ extern unsigned long long g_launches;
 #define __restrict__
 #define __launch_bounds__(...)
 static inline void __syncthreads() { ts_emul::syncthreads(); }
+// warp-level barrier: with one-fiber-per-thread round-robin scheduling a yield gives exactly the needed
+// guarantee (when a thread resumes, every other live thread has passed its previous sync point)
+static inline void __syncwarp() { ts_emul::syncthreads(); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __brev(uint32_t x) {
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);

@@ -129,3 +129,5 @@ def test_pcs_commit(ts, ctx, orc):
 def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
+    pc.check_dot_ext_powers(ts, ctx, orc, 300, 72)   # width % 4 == 0: fast kernel, partial last block
+    pc.check_dot_ext_powers(ts, ctx, orc, 33, 256)
