@@ -27,11 +27,15 @@ struct FastTables {
     int small_log;
 };
 
-// SM: the small tables live in shared memory (plain loads -> LDS); otherwise read-only global loads
-template <bool INV, bool SM>
-TS_D uint2 stw(const FastTables &t, uint32_t e) {
-    const uint2 *p = (INV ? t.tw_small_inv : t.tw_small) + e;
-    return SM ? *p : __ldg(p);
+// Inter-round twiddle of register/digit `i` for butterfly group `g` in a round whose sub-transform has 2^LOGS
+// points and 2^LOGG groups: w_{2^LOGS}^(+-g*u).  SM = false: read-only global load from the 2^small_log table.
+// SM = true (lde_mid): t.tw_small[_inv] point at shared-memory tables laid out [i][g] by fill_round_tables(), so
+// the 32 threads of a warp (consecutive g) read consecutive entries -- conflict free -- whereas indexing a
+// plain power table by g*u would serialise up to 32-way.
+template <bool INV, bool SM, int LOGS, int LOGG>
+TS_D uint2 stw(const FastTables &t, const uint2 *sm_tab, uint32_t g, uint32_t u, uint32_t i) {
+    if (SM) return sm_tab[(i << LOGG) + g];
+    return __ldg((INV ? t.tw_small_inv : t.tw_small) + ((g * u) << (t.small_log - LOGS)));
 }
 template <bool INV>
 TS_D uint2 btw(const FastTables &t, uint32_t e) {
@@ -48,13 +52,13 @@ TS_D uint32_t phys(uint32_t lane, uint32_t p) {
 // M8: radix R = 2^(D-8), elements p = g + 256 c, g = tid & 255.  Optional prescale (lde_mid first round):
 // element c of every lane is multiplied by pos[c] and by the lane scalar.
 template <int D, bool INV, bool PRE, int NT, bool SM>
-TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const uint2 *pw, const uint2 *lane_w,
-                 int tid) {
+TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const uint2 *sm_tab, const uint2 *pw,
+                 const uint2 *lane_w, int tid) {
     constexpr int LOGR = D - 8, R = 1 << LOGR, K = 1 << (14 - D);
     const uint32_t g = tid & 255, sg = g ^ (g >> 4);
     uint2 tw[R];
     TS_UNROLL
-    for (int i = 1; i < R; i++) tw[i] = stw<INV, SM>(t, (g * (uint32_t)brev_c(i, LOGR)) << (t.small_log - D));
+    for (int i = 1; i < R; i++) tw[i] = stw<INV, SM, D, 8>(t, sm_tab, g, (uint32_t)brev_c(i, LOGR), i);
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sg ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t x[R];
@@ -74,13 +78,13 @@ TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const 
 }
 // M4: radix 16 inside blocks of 256: p = 256 blk + g + 16 c
 template <int D, bool INV, int NT, bool SM>
-TS_D void dif_m4(uint32_t *tile, const FastTables &t, int tid) {
+TS_D void dif_m4(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t grp = tid & (G - 1), blk = grp >> 4, g = grp & 15;
     const uint32_t pb = (blk << 8) | ((blk & 1u) << 4) | g;
     uint2 tw[16];
     TS_UNROLL
-    for (int i = 1; i < 16; i++) tw[i] = stw<INV, SM>(t, (g * (uint32_t)brev_c(i, 4)) << (t.small_log - 8));
+    for (int i = 1; i < 16; i++) tw[i] = stw<INV, SM, 8, 4>(t, sm_tab, g, (uint32_t)brev_c(i, 4), i);
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t x[16];
@@ -139,13 +143,13 @@ TS_D void dit_m0(uint32_t *tile, int tid) {
     }
 }
 template <int D, int NT, bool SM>
-TS_D void dit_m4(uint32_t *tile, const FastTables &t, int tid) {
+TS_D void dit_m4(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t grp = tid & (G - 1), blk = grp >> 4, j = grp & 15;
     const uint32_t pb = (blk << 8) | ((blk & 1u) << 4) | j;
     uint2 tw[16];  // for digit c: w_256^-(c j)
     TS_UNROLL
-    for (int c = 1; c < 16; c++) tw[c] = stw<true, SM>(t, ((uint32_t)c * j) << (t.small_log - 8));
+    for (int c = 1; c < 16; c++) tw[c] = stw<true, SM, 8, 4>(t, sm_tab, j, (uint32_t)c, c);
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t v[16];
@@ -159,12 +163,12 @@ TS_D void dit_m4(uint32_t *tile, const FastTables &t, int tid) {
     }
 }
 template <int D, int NT, bool SM>
-TS_D void dit_m8(uint32_t *tile, const FastTables &t, int tid) {
+TS_D void dit_m8(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
     constexpr int LOGR = D - 8, R = 1 << LOGR, K = 1 << (14 - D);
     const uint32_t j = tid & 255, sj = j ^ (j >> 4);
     uint2 tw[R];
     TS_UNROLL
-    for (int c = 1; c < R; c++) tw[c] = stw<true, SM>(t, ((uint32_t)c * j) << (t.small_log - D));
+    for (int c = 1; c < R; c++) tw[c] = stw<true, SM, D, 8>(t, sm_tab, j, (uint32_t)c, c);
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sj ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t v[R];
@@ -256,9 +260,9 @@ __global__ void __launch_bounds__(PASS_NT, 3) ntt_pass_fast_kernel(FastPassParam
     const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo, row_stride = (size_t)1 << p.lo_bits;
     load_tile<D, false, PASS_NT>(tile, p.src, row_base, row_stride, p.width, col0, tid);
     __syncthreads();
-    dif_m8<D, INV, false, PASS_NT, false>(tile, tile, p.t, nullptr, nullptr, tid);
+    dif_m8<D, INV, false, PASS_NT, false>(tile, tile, p.t, nullptr, nullptr, nullptr, tid);
     __syncthreads();
-    dif_m4<D, INV, PASS_NT, false>(tile, p.t, tid);
+    dif_m4<D, INV, PASS_NT, false>(tile, p.t, nullptr, tid);
     uint2 pt[16];  // 3 CTAs per SM overlap this fetch; holding it across rounds would spill at 80 registers
     if (p.lo_bits > 0) load_post_tw<D, INV>(pt, p.t, lo, p.tw_shift, tid);
     __syncthreads();
@@ -286,9 +290,12 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
     TS_DYN_SMEM(uint32_t, smem);
     constexpr int L = 1 << D, K = 1 << (14 - D), R8 = 1 << (D - 8);
     uint32_t *A = smem, *W = smem + K * L;
-    uint2 *twf = reinterpret_cast<uint2 *>(W + K * L);  // shared copies of w_{2^D}^(+-e): twiddle reads become LDS
-    uint2 *twi = twf + L;
-    uint2 *lane_w = twi + L;
+    // shared-memory inter-round twiddle tables, laid out [register i][group g] (see stw):
+    uint2 *f8 = reinterpret_cast<uint2 *>(W + K * L);  // forward M8: w_L^(g brev(i)),   R8 x 256
+    uint2 *f4 = f8 + R8 * 256;                         // forward M4: w_256^(g brev4(i)), 16 x 16
+    uint2 *i8 = f4 + 256;                              // inverse (DIT) M8: w_L^-(c j),  R8 x 256
+    uint2 *i4 = i8 + R8 * 256;                         // inverse (DIT) M4: w_256^-(c j), 16 x 16
+    uint2 *lane_w = i4 + 256;
     const int tid = threadIdx.x;
     const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = blockIdx.x / p.n_col_slices;
     const uint32_t col0 = cs << (14 - D);
@@ -297,20 +304,23 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
     // whole inverse sub-transform
     uint2 pt[16];
     if (p.klo_bits > 0) load_post_tw<D, false>(pt, p.t, Kc, p.tw_shift, tid);
-    for (int i = tid; i < L; i += MID_NT) {
-        twf[i] = __ldg(p.t.tw_small + ((size_t)i << (p.t.small_log - D)));
-        twi[i] = __ldg(p.t.tw_small_inv + ((size_t)i << (p.t.small_log - D)));
+    for (int e = tid; e < R8 * 256; e += MID_NT) {
+        const uint32_t i = e >> 8, g = e & 255;
+        f8[e] = __ldg(p.t.tw_small + ((g * (uint32_t)brev_bits(i, D - 8)) << (p.t.small_log - D)));
+        i8[e] = __ldg(p.t.tw_small_inv + ((g * i) << (p.t.small_log - D)));
     }
-    FastTables ts = p.t;
-    ts.tw_small = twf;
-    ts.tw_small_inv = twi;
-    ts.small_log = D;
+    for (int e = tid; e < 256; e += MID_NT) {
+        const uint32_t i = e >> 4, g = e & 15;
+        f4[e] = __ldg(p.t.tw_small + ((g * (uint32_t)brev_bits(i, 4)) << (p.t.small_log - 8)));
+        i4[e] = __ldg(p.t.tw_small_inv + ((g * i) << (p.t.small_log - 8)));
+    }
+    const FastTables &ts = p.t;
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
     load_tile<D, true, MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.width, col0, tid);
     __syncthreads();
     dit_m0<D, MID_NT>(A, tid);
     __syncthreads();
-    dit_m4<D, MID_NT, true>(A, ts, tid);
+    dit_m4<D, MID_NT, true>(A, ts, i4, tid);
     __syncthreads();
     // coset prescale factors of this thread's first-round elements (k_hi = g + 256 c), fetched one coset ahead
     uint2 pw[R8], pw_next[R8];
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
         TS_UNROLL
         for (int c = 0; c < R8; c++) pw_next[c] = __ldg(p.pre_tab + g + 256 * c);
     }
-    dit_m8<D, MID_NT, true>(A, ts, tid);
+    dit_m8<D, MID_NT, true>(A, ts, i8, tid);
     for (uint32_t j = 0; j < (1u << p.b); j++) {
         if (tid < K) lane_w[tid] = p.lane_tab[((size_t)j << p.klo_bits) + Kc];
         TS_UNROLL
@@ -330,9 +340,9 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
             for (int c = 0; c < R8; c++) pw_next[c] = __ldg(p.pre_tab + ((size_t)(j + 1) << D) + g + 256 * c);
         }
         __syncthreads();  // also orders the last DIT round / the previous coset's store before W is rewritten
-        dif_m8<D, false, true, MID_NT, true>(A, W, ts, pw, lane_w, tid);
+        dif_m8<D, false, true, MID_NT, true>(A, W, ts, f8, pw, lane_w, tid);
         __syncthreads();
-        dif_m4<D, false, MID_NT, true>(W, ts, tid);
+        dif_m4<D, false, MID_NT, true>(W, ts, f4, tid);
         __syncthreads();
         if (p.klo_bits > 0) dif_m0<D, false, true, MID_NT>(W, pt, tid);
         else dif_m0<D, false, false, MID_NT>(W, pt, tid);

@@ -424,7 +424,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         fp.pre_tab = pre;
         fp.lane_tab = lane;
         const size_t blocks = ((size_t)1 << klo) * fp.n_col_slices;
-        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + K) * sizeof(uint2);
+        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + 512 + K) * sizeof(uint2);
         KScope ks(c, TS_K_LDE_MID);
         if (dK == 9) {
             auto kfn = nttf::lde_mid_fast_kernel<9>;
