@@ -200,9 +200,11 @@ int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_mont
 /* LDE written into caller-owned memory (e.g. the send buffer of the all-to-all). */
 int ts_coset_lde_batch_into(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
                             ts_matrix *out);
-/* acc (+)= sum_c alpha^(first_power + c) * m[:, c]; a row shard whose columns arrive as G blocks calls it once
- * per block with first_power = block * block_width. */
-int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
+/* alpha^0 .. alpha^(count-1) (+16 zero entries) as a device matrix, computed once per opening */
+int ts_alpha_powers(ts_ctx *ctx, const uint32_t alpha_monty[4], size_t count, ts_matrix **out);
+/* acc (+)= sum_c alpha^(first_power + c) * m[:, c]; a row shard whose columns arrive as several blocks calls it
+ * once per block with first_power = the block's first global column.  No host synchronisation. */
+int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const ts_matrix *alpha_powers, size_t first_power,
                           ts_matrix *acc, int accumulate);
 /* fold rows [first, first + h_local) of a layer of h_global rows (fold_matrix on a contiguous row range);
  * addend_dev (may be NULL) is the matching slice of the next FRI input. */

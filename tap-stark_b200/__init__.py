@@ -107,6 +107,7 @@ _SIGNATURES = {
     "ts_pcs_get_evaluations_on_domain": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp]),
     "ts_dot_ext_powers": (C.c_int, [_vp, _vp, _vp, _vpp]),
     "ts_coset_lde_batch_into": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint32, _vp]),
+    "ts_alpha_powers": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),

@@ -83,7 +83,7 @@ TS_D void compress_pair(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t
 }
 
 // ---- leaf hashing ---------------------------------------------------------------------------------
-constexpr int MAX_SEG = 8;
+constexpr int MAX_SEG = 32;
 struct Segments {
     const uint32_t *ptr[MAX_SEG];
     uint32_t width[MAX_SEG];
@@ -215,9 +215,17 @@ TS_D void absorb_block(uint32_t (&cv)[8], uint32_t (*stack)[8], int &sp, const u
 // AHEAD and stay in flight during the compression; the words are converted Montgomery -> canonical once,
 // transposed through a warp-private, XOR-swizzled 2 KiB shared buffer (conflict-free STS.128 and LDS.128), and
 // each lane compresses its own row in registers.  No block-wide barrier.
+// Several matrices of EQUAL power-of-two width (the column blocks a rank receives from the all-to-all) are
+// hashed as one row: word cw of the leaf lives in segment cw >> log_seg_w.
+struct FastSegs {
+    const uint32_t *ptr[MAX_SEG];
+    uint32_t seg_w;      // width of every segment
+    int log_seg_w;       // log2(seg_w) when n > 1 (unused for n == 1)
+    int n;
+};
 constexpr int FAST_WARPS = 8;
-__global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(const uint32_t *__restrict__ rows, uint32_t width,
-                                                                        size_t n_leaves, int monty, uint32_t *digests) {
+__global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSegs fs, uint32_t width, size_t n_leaves,
+                                                                        int monty, uint32_t *digests) {
     TS_DYN_SMEM(uint32_t, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ws = sm + warp * 512;
@@ -233,8 +241,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(const u
     TS_UNROLL                                                                                                 \
     for (int k = 0; k < 4; k++) {                                                                             \
         const uint32_t row = r0 + 8 * k, cw = 16u * (blk_) + 4u * sub;                                        \
+        const uint32_t sgi = fs.n > 1 ? (cw >> fs.log_seg_w) : 0u;                                            \
+        const uint32_t off = fs.n > 1 ? (cw & (fs.seg_w - 1u)) : cw;                                          \
         pf[k] = (leaf0 + row < n_leaves && cw < width)                                                        \
-                    ? *reinterpret_cast<const uint4 *>(rows + (leaf0 + row) * width + cw)                     \
+                    ? *reinterpret_cast<const uint4 *>(fs.ptr[sgi] + (leaf0 + row) * fs.seg_w + off)         \
                     : make_uint4(0, 0, 0, 0);                                                                 \
     }
     TS_FETCH(0u)

@@ -499,7 +499,7 @@ int bitrev_rows(ts_ctx *c, const uint32_t *in, uint32_t *out, int log_h, size_t 
 // ---- hashing ------------------------------------------------------------------------------------
 int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::vector<uint32_t> &shifts,
               size_t n_leaves, uint32_t *digests) {
-    if (mats.size() > (size_t)b3::MAX_SEG) TS_FAIL(c, TS_ERR_ARG, "mmcs: more than 8 matrices hashed into one layer");
+    if (mats.size() > (size_t)b3::MAX_SEG) TS_FAIL(c, TS_ERR_ARG, "mmcs: more than 32 matrices hashed into one layer");
     if (mats.size() == 1 && shifts[0] == 0 && mats[0]->width <= 16) {
         KScope ks(c, TS_K_HASH_LEAVES);
         auto kfn = b3::hash_leaves_small_kernel;
@@ -507,15 +507,29 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
                   (uint32_t)mats[0]->width, n_leaves, 1, digests);
         return check_launch(c, "hash_leaves_small_kernel");
     }
-    if (mats.size() == 1 && shifts[0] == 0 && (mats[0]->width & 3) == 0 && mats[0]->width <= (256u << b3::MAX_STACK) &&
-        getenv("TS_NO_FAST") == nullptr) {
-        KScope ks(c, TS_K_HASH_LEAVES);
-        auto kfn = b3::hash_rows_fast_kernel;
-        const size_t per_block = (size_t)b3::FAST_WARPS * 32;
-        TS_LAUNCH(kfn, (unsigned)((n_leaves + per_block - 1) / per_block), b3::FAST_WARPS * 32,
-                  (size_t)b3::FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)mats[0]->d, (uint32_t)mats[0]->width,
-                  n_leaves, 1, digests);
-        return check_launch(c, "hash_rows_fast_kernel");
+    {
+        // fast path: one matrix, or several of equal power-of-two width (multi-GPU column blocks), one row per leaf
+        bool fast = getenv("TS_NO_FAST") == nullptr && (mats[0]->width & 3) == 0;
+        size_t total = 0;
+        for (size_t i = 0; i < mats.size() && fast; i++) {
+            fast = shifts[i] == 0 && mats[i]->width == mats[0]->width;
+            total += mats[i]->width;
+        }
+        if (fast && mats.size() > 1) fast = (mats[0]->width & (mats[0]->width - 1)) == 0 && mats[0]->width >= 16;
+        if (fast && total <= ((size_t)256 << b3::MAX_STACK)) {
+            b3::FastSegs fs;
+            for (int i = 0; i < b3::MAX_SEG; i++) fs.ptr[i] = i < (int)mats.size() ? mats[i]->d : nullptr;
+            fs.n = (int)mats.size();
+            fs.seg_w = (uint32_t)mats[0]->width;
+            fs.log_seg_w = 0;
+            while ((1u << fs.log_seg_w) < fs.seg_w) fs.log_seg_w++;
+            KScope ks(c, TS_K_HASH_LEAVES);
+            auto kfn = b3::hash_rows_fast_kernel;
+            const size_t per_block = (size_t)b3::FAST_WARPS * 32;
+            TS_LAUNCH(kfn, (unsigned)((n_leaves + per_block - 1) / per_block), b3::FAST_WARPS * 32,
+                      (size_t)b3::FAST_WARPS * 512 * 4, c->stream, fs, (uint32_t)total, n_leaves, 1, digests);
+            return check_launch(c, "hash_rows_fast_kernel");
+        }
     }
     b3::Segments sg;
     sg.n = (int)mats.size();
@@ -1248,63 +1262,51 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, si
     ts_matrix_free(tmp);
     return rc;
 }
-static int dot_ext_powers_impl(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
-                               ts_matrix *o, int accumulate) {
-    const size_t wpad = (m->width + 15) & ~(size_t)15;  // zero padding: the fast kernel reads whole 16-column blocks
-    std::vector<uint32_t> apow(wpad * 4, 0u);
-    uint32_t a[4], cur[4] = {1, 0, 0, 0}, base[4];
-    for (int i = 0; i < 4; i++) a[i] = h_from_monty(alpha_monty[i]);
-    memcpy(base, a, 16);
-    for (size_t e = first_power; e; e >>= 1) {  // cur = alpha^first_power
-        uint32_t t[4];
-        if (e & 1) {
-            h_ef_mul(cur, base, t);
-            memcpy(cur, t, 16);
-        }
-        h_ef_mul(base, base, t);
-        memcpy(base, t, 16);
+// apow_dev: device array of alpha^(k) for the columns of m (Montgomery EF, one uint4 per column), readable for
+// roundup16(width) entries (columns past the width are multiplied by zero-filled data)
+static int dot_ext_powers_launch(ts_ctx *c, const ts_matrix *m, const uint32_t *apow_dev, ts_matrix *o, int accumulate) {
+    KScope ks(c, TS_K_MISC);
+    if ((m->width & 3) == 0 && getenv("TS_NO_FAST") == nullptr) {
+        auto kfn = fold::dot_rows_fast_kernel;
+        const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
+        TS_LAUNCH(kfn, (unsigned)((m->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
+                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)m->d, m->rows, (uint32_t)m->width,
+                  (const uint4 *)apow_dev, (uint4 *)o->d, accumulate);
+        return check_launch(c, "dot_rows_fast_kernel");
     }
-    for (size_t k = 0; k < m->width; k++) {
+    auto kfn = fold::dot_ext_powers_kernel;
+    TS_LAUNCH(kfn, (unsigned)((m->rows + fold::DOT_ROWS - 1) / fold::DOT_ROWS), 256,
+              (size_t)fold::DOT_ROWS * (fold::DOT_COLS + 1) * 4, c->stream, (const uint32_t *)m->d, m->rows,
+              (uint32_t)m->width, (const uint4 *)apow_dev, (uint4 *)o->d, accumulate);
+    return check_launch(c, "dot_ext_powers_kernel");
+}
+// alpha^0 .. alpha^(count-1) followed by 16 zero entries, as a (count+16) x 4 device matrix
+int ts_alpha_powers(ts_ctx *c, const uint32_t alpha_monty[4], size_t count, ts_matrix **out) {
+    std::vector<uint32_t> apow((count + 16) * 4, 0u);
+    uint32_t a[4], cur[4] = {1, 0, 0, 0};
+    for (int i = 0; i < 4; i++) a[i] = h_from_monty(alpha_monty[i]);
+    for (size_t k = 0; k < count; k++) {
         for (int i = 0; i < 4; i++) apow[4 * k + i] = h_to_monty(cur[i]);
         uint32_t nx[4];
         h_ef_mul(cur, a, nx);
         memcpy(cur, nx, 16);
     }
     ts_matrix *ap = nullptr;
-    TS_TRY(ts_matrix_from_host(c, apow.data(), wpad, 4, &ap));
-    int rc;
-    if ((m->width & 3) == 0 && getenv("TS_NO_FAST") == nullptr) {
-        KScope ks(c, TS_K_MISC);
-        auto kfn = fold::dot_rows_fast_kernel;
-        const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
-        TS_LAUNCH(kfn, (unsigned)((m->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
-                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)m->d, m->rows, (uint32_t)m->width,
-                  (const uint4 *)ap->d, (uint4 *)o->d, accumulate);
-        rc = check_launch(c, "dot_rows_fast_kernel");
-    } else {
-        KScope ks(c, TS_K_MISC);
-        auto kfn = fold::dot_ext_powers_kernel;
-        TS_LAUNCH(kfn, (unsigned)((m->rows + fold::DOT_ROWS - 1) / fold::DOT_ROWS), 256,
-                  (size_t)fold::DOT_ROWS * (fold::DOT_COLS + 1) * 4, c->stream, (const uint32_t *)m->d, m->rows,
-                  (uint32_t)m->width, (const uint4 *)ap->d, (uint4 *)o->d, accumulate);
-        rc = check_launch(c, "dot_ext_powers_kernel");
+    TS_TRY(ts_matrix_from_host(c, apow.data(), count + 16, 4, &ap));
+    cudaError_t e = cudaStreamSynchronize(c->stream);  // apow is a stack-lifetime pageable buffer
+    if (e != cudaSuccess) {
+        ts_matrix_free(ap);
+        TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
     }
-    // `apow` (pageable host memory) was consumed by a stream-ordered copy; the device copy returns to the
-    // stream-ordered pool, so no synchronisation is needed here
-    if (rc == TS_OK) {
-        cudaError_t e = cudaStreamSynchronize(c->stream);  // apow is a stack-lifetime host buffer
-        if (e != cudaSuccess) {
-            c->err = cudaGetErrorString(e);
-            rc = TS_ERR_CUDA;
-        }
-    }
-    ts_matrix_free(ap);
-    return rc;
+    *out = ap;
+    return TS_OK;
 }
 int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out) {
-    ts_matrix *o = nullptr;
-    TS_TRY(new_matrix(c, m->rows, 4, &o));
-    int rc = dot_ext_powers_impl(c, m, alpha_monty, 0, o, 0);
+    ts_matrix *o = nullptr, *ap = nullptr;
+    TS_TRY(ts_alpha_powers(c, alpha_monty, m->width, &ap));
+    int rc = new_matrix(c, m->rows, 4, &o);
+    if (rc == TS_OK) rc = dot_ext_powers_launch(c, m, ap->d, o, 0);
+    ts_matrix_free(ap);  // returns to the stream-ordered pool: safe while the kernel is still queued
     if (rc != TS_OK) {
         ts_matrix_free(o);
         return rc;
@@ -1312,10 +1314,12 @@ int ts_dot_ext_powers(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[
     *out = o;
     return TS_OK;
 }
-int ts_dot_ext_powers_acc(ts_ctx *c, const ts_matrix *m, const uint32_t alpha_monty[4], size_t first_power,
+int ts_dot_ext_powers_acc(ts_ctx *c, const ts_matrix *m, const ts_matrix *alpha_powers, size_t first_power,
                           ts_matrix *acc, int accumulate) {
     if (acc->rows != m->rows || acc->width != 4) TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_acc: acc must be rows x 4");
-    return dot_ext_powers_impl(c, m, alpha_monty, first_power, acc, accumulate);
+    if (alpha_powers->width != 4 || first_power + ((m->width + 15) & ~(size_t)15) > alpha_powers->rows)
+        TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_acc: alpha_powers too short (use ts_alpha_powers(total_width))");
+    return dot_ext_powers_launch(c, m, alpha_powers->d + 4 * first_power, acc, accumulate);
 }
 
 // ---------------------------------------------------------------- sharded (multi-GPU) building blocks

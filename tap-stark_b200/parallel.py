@@ -79,35 +79,64 @@ class ShardedProver:
         return layer[0]
 
     # ---- the step -------------------------------------------------------------------------------------
+    REPLICATE_BELOW = 1 << 20  # FRI layers of at most this many elements are gathered and folded on every rank
+
+    def _chunks(self, wl: int) -> int:
+        """column chunks per rank: the LDE of chunk c+1 overlaps the all-to-all of chunk c (NCCL runs on its own
+        stream).  Chunk widths stay powers of two >= 16 so the received blocks feed the fast leaf kernel."""
+        c = 1
+        while c < 4 and wl % (2 * c) == 0 and wl // (2 * c) >= 16 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
+            c *= 2
+        return c if self.world > 1 else 1
+
     def commit_and_fri(self, trace_t):
         """trace_t: torch int32 [n, w/G] -- this rank's columns of the trace (Montgomery-form bits).
         Returns dict(root, commits, final_poly, rounds); identical on every rank."""
-        ts, ctx, torch, G, r, b = self.ts, self.ctx, self.torch, self.world, self.rank, self.b
+        ts, ctx, torch, dist, G, r, b = self.ts, self.ctx, self.torch, self.dist, self.world, self.rank, self.b
         L = ctx._L
         n, wl = trace_t.shape
         N = n << b
         Nl = N // G
-        ev = self._wrap(trace_t, n, wl)
-        lde_t = torch.empty((N, wl), dtype=torch.int32, device=self.device)
-        lde = self._wrap(lde_t, N, wl)
+        C_ = self._chunks(wl)
+        wc = wl // C_
         gen = int(ts.to_monty(ts.GENERATOR))
-        ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
-        # re-shard by rows
-        recv_t = torch.empty((G, Nl, wl), dtype=torch.int32, device=self.device)
-        self.exchange(list(lde_t.view(G, Nl, wl).unbind(0)), list(recv_t.unbind(0)))
-        del lde, lde_t
-        blocks = [self._wrap(recv_t[s], Nl, wl) for s in range(G)]
+        recv, works, keep = [], [], []
+        for c in range(C_):
+            src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
+            ev = self._wrap(src_t, n, wc)
+            lde_t = torch.empty((N, wc), dtype=torch.int32, device=self.device)
+            lde = self._wrap(lde_t, N, wc)
+            ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
+            recv_t = torch.empty((G, Nl, wc), dtype=torch.int32, device=self.device)
+            send_list, recv_list = list(lde_t.view(G, Nl, wc).unbind(0)), list(recv_t.unbind(0))
+            if self.use_batched_p2p:
+                self.exchange(send_list, recv_list)
+            else:
+                works.append(dist.all_to_all(recv_list, send_list, async_op=True))  # overlaps the next chunk's LDE
+            recv.append(recv_t)
+            keep.append((lde_t, src_t))
+        for w_ in works:
+            w_.wait()
+        del keep
+        # global column order: rank-major, then chunk
+        blocks, first_col = [], []
+        for s_ in range(G):
+            for c in range(C_):
+                blocks.append(self._wrap(recv[c][s_], Nl, wc))
+                first_col.append(s_ * wl + c * wc)
         sub_root, data = self.mmcs.commit(blocks)
         root = self.combine_roots(sub_root)
         ch = ts.BfChallenger()
         ch.observe(root)
         alpha = ch.sample()
         am = ts.to_monty(alpha)
+        ap = C.c_void_p()
+        ctx.check(L.ts_alpha_powers(ctx._h, am.ctypes.data_as(C.c_void_p), wl * G, C.byref(ap)), "alpha_powers")
         fri_t = torch.empty((Nl, 4), dtype=torch.int32, device=self.device)
         fri = self._wrap(fri_t, Nl, 4)
-        for s in range(G):
-            ctx.check(L.ts_dot_ext_powers_acc(ctx._h, blocks[s]._h, am.ctypes.data_as(C.c_void_p), s * wl, fri._h,
-                                              int(s > 0)), "dot_ext_powers_acc")
+        for i, blk in enumerate(blocks):
+            ctx.check(L.ts_dot_ext_powers_acc(ctx._h, blk._h, ap, first_col[i], fri._h, int(i > 0)), "dot_ext_powers_acc")
+        L.ts_matrix_free(ap)
         data.free()
         commits, final = self._fri_commit_phase(fri_t, N, ch)
         return {"root": root, "commits": commits, "final_poly": final, "rounds": len(commits)}
@@ -121,7 +150,7 @@ class ShardedProver:
         blowup = 1 << self.b
         while len_g > blowup:
             h_g, h_l = len_g // 2, local // 2
-            if h_l >= 256 and h_l * G == h_g:
+            if len_g > self.REPLICATE_BELOW and h_l >= 256 and h_l * G == h_g:
                 leaves = self._wrap(cur_t, h_l, 8)
                 sub, data = self.mmcs.commit([leaves])
                 root = self.combine_roots(sub)
@@ -133,10 +162,9 @@ class ShardedProver:
                 ctx.check(L.ts_fri_fold_ext_shard(ctx._h, C.c_void_p(cur_t.data_ptr()), h_g, r * h_l, h_l,
                                                   beta.ctypes.data_as(C.c_void_p), None, C.c_void_p(out_t.data_ptr())),
                           "fri_fold_ext_shard")
-                ctx.synchronize()  # cur_t may be released by torch's allocator on rebinding
                 cur_t, len_g, local = out_t, h_g, h_l
                 continue
-            # small layer: gather it everywhere and finish replicated
+            # small layer: gather it everywhere and finish replicated (no further communication)
             parts = [torch.empty_like(cur_t) for _ in range(G)]
             dist.all_gather(parts, cur_t)
             full_t = torch.cat(parts, dim=0).contiguous()

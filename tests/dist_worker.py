@@ -33,6 +33,7 @@ def main():
     shard = ts.to_monty(np.ascontiguousarray(trace[:, rank * wl : (rank + 1) * wl]))
     shard_t = torch.from_numpy(shard.view(np.int32).copy())
     prover = ShardedProver(ts, ctx, rank, world, b, torch.device("cpu"))
+    prover.REPLICATE_BELOW = int(os.environ.get("TS_REPLICATE_BELOW", "64"))  # exercise the row-sharded FRI rounds
     res = prover.commit_and_fri(shard_t)
     res["root"] = res["root"].hex()
     res["commits"] = [c.hex() for c in res["commits"]]

@@ -54,7 +54,7 @@ def oracle_transcript(orc, log_n, width, b):
     return tree.root.hex(), [c.hex() for c in res["commits"]], res["final_poly"].tolist()
 
 
-@pytest.mark.parametrize("world,log_n,width,b", [(2, 10, 8, 2), (4, 11, 8, 1), (2, 6, 4, 2)])
+@pytest.mark.parametrize("world,log_n,width,b", [(2, 10, 8, 2), (4, 11, 8, 1), (2, 6, 4, 2), (2, 9, 64, 1)])
 def test_sharded_matches_oracle(tmp_path, orc, world, log_n, width, b):
     results = run_world(tmp_path, world, log_n, width, b)
     root, commits, final = oracle_transcript(orc, log_n, width, b)
