@@ -185,8 +185,7 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner/debug off stdout: ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
         build_device()

@@ -188,8 +188,8 @@ TS_D void dit_m8(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int t
 // ---- tile I/O: uint4 = 4 adjacent columns of one row ------------------------------------------------------
 // BREV: tile position q holds source row index brev_D(q) (the DIT input order of lde_mid)
 template <int D, bool BREV, int NT>
-TS_D void load_tile(uint32_t *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t width,
-                    uint32_t col0, int tid) {
+TS_D void load_tile(uint32_t *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch,
+                    uint32_t ncols, uint32_t col0, int tid) {
     constexpr int LOGV = 12 - D, NV = 1 << LOGV;  // vectors per position (K/4)
     constexpr int TOTAL = (1 << D) * NV;
     TS_UNROLL
@@ -201,8 +201,8 @@ TS_D void load_tile(uint32_t *tile, const uint32_t *src, size_t row_base, size_t
             const uint32_t v = it & (NV - 1), q = it >> LOGV;
             const uint32_t r = BREV ? brev_bits(q, D) : q;
             const uint32_t col = col0 + 4 * v;
-            val[u] = (it < TOTAL && col < width)
-                         ? *reinterpret_cast<const uint4 *>(src + (row_base + (size_t)r * row_stride) * width + col)
+            val[u] = (it < TOTAL && col < ncols)
+                         ? *reinterpret_cast<const uint4 *>(src + (row_base + (size_t)r * row_stride) * pitch + col)
                          : make_uint4(0, 0, 0, 0);
         }
         TS_UNROLL
@@ -219,29 +219,31 @@ TS_D void load_tile(uint32_t *tile, const uint32_t *src, size_t row_base, size_t
     }
 }
 template <int D, int NT>
-TS_D void store_tile(const uint32_t *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t width,
-                     uint32_t col0, int tid) {
+TS_D void store_tile(const uint32_t *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t pitch,
+                     uint32_t ncols, uint32_t col0, int tid) {
     constexpr int LOGV = 12 - D, NV = 1 << LOGV;
     constexpr int TOTAL = (1 << D) * NV;
     for (int it = tid; it < TOTAL; it += NT) {
         const uint32_t v = it & (NV - 1), q = it >> LOGV;
         const uint32_t col = col0 + 4 * v;
-        if (col < width) {
+        if (col < ncols) {
             uint4 o;
             o.x = tile[phys<D>(4 * v + 0, q)];
             o.y = tile[phys<D>(4 * v + 1, q)];
             o.z = tile[phys<D>(4 * v + 2, q)];
             o.w = tile[phys<D>(4 * v + 3, q)];
-            *reinterpret_cast<uint4 *>(dst + (row_base + (size_t)q * row_stride) * width + col) = o;
+            *reinterpret_cast<uint4 *>(dst + (row_base + (size_t)q * row_stride) * pitch + col) = o;
         }
     }
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------
+// src/dst point at the first column of the window being transformed (a column chunk of a wider matrix is a
+// window: pitch = row stride in u32, ncols = window width), so chunks can be pipelined against H2D copies.
 struct FastPassParams {
     const uint32_t *src;
     uint32_t *dst;
-    uint32_t width;
+    uint32_t src_pitch, dst_pitch, ncols;
     int lo_bits, hi_bits;
     uint32_t n_col_slices;
     int tw_shift;  // big_log - (lo_bits + D)
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(PASS_NT, 3) ntt_pass_fast_kernel(FastPassParam
     const uint32_t lo = tile_id & ((1u << p.lo_bits) - 1), hi = tile_id >> p.lo_bits;
     const uint32_t col0 = cs << (14 - D);
     const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo, row_stride = (size_t)1 << p.lo_bits;
-    load_tile<D, false, PASS_NT>(tile, p.src, row_base, row_stride, p.width, col0, tid);
+    load_tile<D, false, PASS_NT>(tile, p.src, row_base, row_stride, p.src_pitch, p.ncols, col0, tid);
     __syncthreads();
     dif_m8<D, INV, false, PASS_NT, false>(tile, tile, p.t, nullptr, nullptr, nullptr, tid);
     __syncthreads();
@@ -269,13 +271,13 @@ __global__ void __launch_bounds__(PASS_NT, 3) ntt_pass_fast_kernel(FastPassParam
     if (p.lo_bits > 0) dif_m0<D, INV, true, PASS_NT>(tile, pt, tid);
     else dif_m0<D, INV, false, PASS_NT>(tile, pt, tid);
     __syncthreads();
-    store_tile<D, PASS_NT>(tile, p.dst, row_base, row_stride, p.width, col0, tid);
+    store_tile<D, PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.ncols, col0, tid);
 }
 
 struct FastMidParams {
     const uint32_t *src;
     uint32_t *dst;
-    uint32_t width;
+    uint32_t src_pitch, dst_pitch, ncols;
     int klo_bits, b;
     uint32_t n_col_slices;
     int tw_shift;  // big_log - m
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
     }
     const FastTables &ts = p.t;
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
-    load_tile<D, true, MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.width, col0, tid);
+    load_tile<D, true, MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.src_pitch, p.ncols, col0, tid);
     __syncthreads();
     dit_m0<D, MID_NT>(A, tid);
     __syncthreads();
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p
         if (p.klo_bits > 0) dif_m0<D, false, true, MID_NT>(W, pt, tid);
         else dif_m0<D, false, false, MID_NT>(W, pt, tid);
         __syncthreads();
-        store_tile<D, MID_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.width, col0, tid);
+        store_tile<D, MID_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
+                              p.ncols, col0, tid);
     }
 }
 

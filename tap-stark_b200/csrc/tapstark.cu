@@ -42,6 +42,13 @@ struct ts_ctx {
     size_t scratch_words = 0;
     // stream-ordered caching allocator: freed blocks are reused by later work on the same stream without a
     // device synchronisation (cudaFree would serialise every step of the pipeline)
+    // H2D pipeline of the host-buffer entry points: column chunks are copied on copy_stream while the previous
+    // chunk's LDE runs on `stream`
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool ev_free_used[2] = {false, false};
+    uint32_t *stage[2] = {nullptr, nullptr};
+    size_t stage_words = 0;
     std::multimap<size_t, void *> pool_free;
     std::map<void *, size_t> pool_sizes;
     // stats
@@ -258,13 +265,19 @@ int launch_pass_fast(ts_ctx *c, bool inverse, const nttf::FastPassParams &p, siz
     return check_launch(c, "ntt_pass_fast_kernel");
 }
 
+// w columns are transformed; src_pitch/dst_pitch (0 = w) are the row strides when src/dst are column windows of
+// wider matrices (fast path only)
 int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, size_t w, int d, int lo_bits,
-                int hi_bits, bool has_scale, uint2 scale) {
+                int hi_bits, bool has_scale, uint2 scale, size_t src_pitch = 0, size_t dst_pitch = 0) {
+    if (!src_pitch) src_pitch = w;
+    if (!dst_pitch) dst_pitch = w;
     if (!has_scale && fast_shape(d, w)) {
         nttf::FastPassParams fp;
         fp.src = src;
         fp.dst = dst;
-        fp.width = (uint32_t)w;
+        fp.src_pitch = (uint32_t)src_pitch;
+        fp.dst_pitch = (uint32_t)dst_pitch;
+        fp.ncols = (uint32_t)w;
         fp.lo_bits = lo_bits;
         fp.hi_bits = hi_bits;
         const size_t K = (size_t)1 << (14 - d);
@@ -278,6 +291,7 @@ int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, siz
             default: return launch_pass_fast<11>(c, inverse, fp, blocks);
         }
     }
+    if (src_pitch != w || dst_pitch != w) TS_FAIL(c, TS_ERR_ARG, "column windows need the fast NTT path");
     ntt::PassParams p;
     p.src = src;
     p.dst = dst;
@@ -381,10 +395,23 @@ int get_coset_tables(ts_ctx *c, int m, int b, int d, uint32_t shift_monty, uint2
 }
 
 // dst (n << b) x w  <-  committed-order coset LDE of src (n x w)
+bool all_digits_fast(int m, size_t w) {
+    const std::vector<int> dg = split_digits(m);
+    if (dg.empty()) return false;
+    for (int d : dg)
+        if (!fast_shape(d, w)) return false;
+    return true;
+}
+
+// windows: src is n x w with row stride src_pitch, dst is (n<<b) x w with row stride dst_pitch (0 = w)
 int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty,
-                  uint32_t *dst) {
+                  uint32_t *dst, size_t src_pitch = 0, size_t dst_pitch = 0) {
+    if (!src_pitch) src_pitch = w;
+    if (!dst_pitch) dst_pitch = w;
     const int m = log2_strict(n);
     if (m < 0 || w == 0 || m + (int)b > 27) TS_FAIL(c, TS_ERR_ARG, "lde: rows must be a power of two, rows<<added_bits <= 2^27");
+    if ((src_pitch != w || dst_pitch != w) && !all_digits_fast(m, w))
+        TS_FAIL(c, TS_ERR_ARG, "column windows need the fast NTT path");
     if (m == 0) {
         KScope ks(c, TS_K_MISC);
         auto kfn = ntt::broadcast_row_kernel;
@@ -406,7 +433,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
     for (size_t i = 0; i + 1 < D; i++) {
         const int lo_bits = m - used - dg[i];
         TS_TRY(launch_pass(c, true, i == 0 ? src : c->scratch, c->scratch, w, dg[i], lo_bits, used, false,
-                           make_uint2(0, 0)));
+                           make_uint2(0, 0), i == 0 ? src_pitch : w, w));
         used += dg[i];
     }
     // middle kernel
@@ -414,7 +441,9 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         nttf::FastMidParams fp;
         fp.src = D > 1 ? c->scratch : src;
         fp.dst = dst;
-        fp.width = (uint32_t)w;
+        fp.src_pitch = (uint32_t)(D > 1 ? w : src_pitch);
+        fp.dst_pitch = (uint32_t)dst_pitch;
+        fp.ncols = (uint32_t)w;
         fp.klo_bits = klo;
         fp.b = (int)b;
         const size_t K = (size_t)1 << (14 - dK);
@@ -469,8 +498,64 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
     for (size_t i = 0; i + 1 < D; i++) {
         const int lo_bits = klo - used - dg[i];
         const int hi_bits = m + (int)b - lo_bits - dg[i];
-        TS_TRY(launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0)));
+        TS_TRY(launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), dst_pitch, dst_pitch));
         used += dg[i];
+    }
+    return TS_OK;
+}
+
+// Host trace -> committed LDE on the device, H2D overlapped with compute: the matrix is cut into column chunks;
+// chunk k+1 is copied (strided 2-D copy out of the row-major host matrix) while chunk k is transformed.  Columns
+// are independent polynomials, so the result is identical to the one-shot LDE.
+size_t chunk_cols() {
+    if (const char *e = getenv("TS_CHUNK_COLS")) return (size_t)strtoul(e, nullptr, 10);  // test hook
+    return 64;
+}
+bool pipeline_eligible(size_t n, size_t w) {
+    const int m = log2_strict(n);
+    const size_t wc = chunk_cols();
+    return m >= 18 && wc >= 8 && w >= 2 * wc && (w & 3) == 0 && all_digits_fast(m, wc) &&
+           (w % wc == 0 || all_digits_fast(m, w % wc)) && getenv("TS_NO_PIPELINE") == nullptr;
+}
+int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w, unsigned b, uint32_t shift_monty,
+                            uint32_t *dst) {
+    const size_t wc = chunk_cols(), nchunks = (w + wc - 1) / wc;
+    if (c->stage_words < n * wc) {
+        TS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int s = 0; s < 2; s++) {
+            if (c->stage[s]) cudaFree(c->stage[s]);
+            c->stage[s] = nullptr;
+            TS_CUDA(c, cudaMalloc((void **)&c->stage[s], n * wc * 4));
+            c->ev_free_used[s] = false;
+        }
+        c->stage_words = n * wc;
+    }
+#ifndef TS_EMULATE
+    if (!c->copy_stream) {
+        TS_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; s++) {
+            TS_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy[s], cudaEventDisableTiming));
+            TS_CUDA(c, cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming));
+        }
+    }
+#endif
+    for (size_t ch = 0; ch < nchunks; ch++) {
+        const int s = (int)(ch & 1);
+        const size_t cols = std::min(wc, w - ch * wc);
+#ifndef TS_EMULATE
+        if (c->ev_free_used[s]) TS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
+#endif
+        TS_CUDA(c, cudaMemcpy2DAsync(c->stage[s], cols * 4, host + ch * wc, w * 4, cols * 4, n, cudaMemcpyHostToDevice,
+                                     c->copy_stream));
+#ifndef TS_EMULATE
+        TS_CUDA(c, cudaEventRecord(c->ev_copy[s], c->copy_stream));
+        TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[s], 0));
+#endif
+        TS_TRY(lde_committed(c, c->stage[s], n, cols, b, shift_monty, dst + ch * wc, cols, w));
+#ifndef TS_EMULATE
+        TS_CUDA(c, cudaEventRecord(c->ev_free[s], c->stream));
+        c->ev_free_used[s] = true;
+#endif
     }
     return TS_OK;
 }
@@ -793,6 +878,18 @@ void ts_ctx_destroy(ts_ctx *c) {
     cudaFree(c->tw_big);
     cudaFree(c->fold_tlo);
     cudaFree(c->scratch);
+    cudaFree(c->stage[0]);
+    cudaFree(c->stage[1]);
+#ifndef TS_EMULATE
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int s = 0; s < 2; s++) {
+            cudaEventDestroy(c->ev_copy[s]);
+            cudaEventDestroy(c->ev_free[s]);
+        }
+        cudaStreamDestroy(c->copy_stream);
+    }
+#endif
     pool_trim(c);
     for (auto &kv : c->coset_tabs) {
         cudaFree(kv.second.first);
@@ -954,8 +1051,14 @@ int ts_coset_dft_batch(ts_ctx *c, const ts_matrix *coeffs, uint32_t shift_monty,
 int ts_coset_lde_batch_host(ts_ctx *c, const uint32_t *evals_host, size_t rows, size_t width, unsigned added_bits,
                             uint32_t shift_monty, int natural_order, uint32_t *out_host) {
     ts_matrix *in = nullptr, *o = nullptr;
-    TS_TRY(ts_matrix_from_host(c, evals_host, rows, width, &in));
-    int rc = ts_coset_lde_batch(c, in, added_bits, shift_monty, natural_order, &o);
+    int rc;
+    if (!natural_order && log2_strict(rows) >= 0 && pipeline_eligible(rows, width)) {
+        rc = new_matrix(c, rows << added_bits, width, &o);
+        if (rc == TS_OK) rc = lde_from_host_pipelined(c, evals_host, rows, width, added_bits, shift_monty, o->d);
+    } else {
+        TS_TRY(ts_matrix_from_host(c, evals_host, rows, width, &in));
+        rc = ts_coset_lde_batch(c, in, added_bits, shift_monty, natural_order, &o);
+    }
     if (rc == TS_OK) rc = ts_matrix_download(c, o, 0, o->rows, out_host);
     ts_matrix_free(in);
     ts_matrix_free(o);
@@ -1243,11 +1346,32 @@ int ts_pcs_commit(ts_ctx *c, ts_matrix *const *evals, const uint32_t *domain_shi
 int ts_pcs_commit_host(ts_ctx *c, const uint32_t *const *evals_host, const size_t *rows, const size_t *widths,
                        const uint32_t *domain_shifts_monty, size_t n, unsigned log_blowup, int layout,
                        uint8_t root[32], ts_tree **out) {
-    std::vector<ts_matrix *> in(n, nullptr);
+    std::vector<ts_matrix *> ldes;
     int rc = TS_OK;
-    for (size_t i = 0; i < n && rc == TS_OK; i++) rc = ts_matrix_from_host(c, evals_host[i], rows[i], widths[i], &in[i]);
-    if (rc == TS_OK) rc = ts_pcs_commit(c, in.data(), domain_shifts_monty, n, log_blowup, layout, root, out);
-    for (ts_matrix *m : in) ts_matrix_free(m);
+    for (size_t i = 0; i < n && rc == TS_OK; i++) {
+        const uint32_t dshift = h_from_monty(domain_shifts_monty[i]);
+        if (dshift == 0 || log2_strict(rows[i]) < 0) {
+            c->err = "pcs commit: bad domain";
+            rc = TS_ERR_ARG;
+            break;
+        }
+        const uint32_t shift = h_to_monty(bb::cmul(31, bb::cinv(dshift)));  // two_adic_pcs.rs:235
+        ts_matrix *lde = nullptr;
+        if (pipeline_eligible(rows[i], widths[i])) {
+            rc = new_matrix(c, rows[i] << log_blowup, widths[i], &lde);
+            if (rc == TS_OK) rc = lde_from_host_pipelined(c, evals_host[i], rows[i], widths[i], log_blowup, shift, lde->d);
+        } else {
+            ts_matrix *in = nullptr;
+            rc = ts_matrix_from_host(c, evals_host[i], rows[i], widths[i], &in);
+            if (rc == TS_OK) rc = ts_coset_lde_batch(c, in, log_blowup, shift, 0, &lde);
+            ts_matrix_free(in);
+        }
+        if (rc == TS_OK) ldes.push_back(lde);
+        else ts_matrix_free(lde);
+    }
+    if (rc == TS_OK) rc = mmcs_commit(c, ldes.data(), ldes.size(), layout, 1, root, out, true);
+    if (rc != TS_OK)
+        for (ts_matrix *m : ldes) ts_matrix_free(m);
     return rc;
 }
 int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, size_t domain_size, uint32_t *out_host) {

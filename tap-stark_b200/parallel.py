@@ -89,20 +89,57 @@ class ShardedProver:
             c *= 2
         return c if self.world > 1 else 1
 
-    def commit_and_fri(self, trace_t):
-        """trace_t: torch int32 [n, w/G] -- this rank's columns of the trace (Montgomery-form bits).
+    def host_panels(self, trace_t):
+        """Pinned host copy of this rank's shard as column panels (one contiguous [n, wc] tensor per chunk): the
+        layout a column-sharded host prover hands over, so that panel c+1 is copied while panel c is transformed."""
+        torch = self.torch
+        n, wl = trace_t.shape
+        C_ = self._chunks(wl)
+        wc = wl // C_
+        panels = []
+        for c in range(C_):
+            t = torch.empty((n, wc), dtype=torch.int32, pin_memory=True)
+            t.copy_(trace_t[:, c * wc : (c + 1) * wc])
+            panels.append(t)
+        return panels
+
+    def commit_and_fri(self, trace_t, host_panels=None):
+        """trace_t: torch int32 [n, w/G] -- this rank's columns of the trace (Montgomery-form bits), resident; or
+        host_panels (see host_panels()): the same data in pinned host memory, copied H2D inside the step.
         Returns dict(root, commits, final_poly, rounds); identical on every rank."""
         ts, ctx, torch, dist, G, r, b = self.ts, self.ctx, self.torch, self.dist, self.world, self.rank, self.b
         L = ctx._L
-        n, wl = trace_t.shape
+        if host_panels is not None:
+            n, wl = host_panels[0].shape[0], sum(p_.shape[1] for p_ in host_panels)
+        else:
+            n, wl = trace_t.shape
         N = n << b
         Nl = N // G
         C_ = self._chunks(wl)
         wc = wl // C_
         gen = int(ts.to_monty(ts.GENERATOR))
         recv, works, keep = [], [], []
+        staged = []
+        if host_panels is not None:
+            # all panels are queued on a side stream up front; the main stream waits panel by panel
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream()
+            main = torch.cuda.current_stream()
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                for c in range(C_):
+                    d_ = torch.empty((n, wc), dtype=torch.int32, device=self.device)
+                    d_.copy_(host_panels[c], non_blocking=True)
+                    e_ = torch.cuda.Event()
+                    e_.record(self._copy_stream)
+                    d_.record_stream(main)
+                    staged.append((d_, e_))
         for c in range(C_):
-            src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
+            if host_panels is not None:
+                src_t, ev_ = staged[c]
+                torch.cuda.current_stream().wait_event(ev_)
+            else:
+                src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
             ev = self._wrap(src_t, n, wc)
             lde_t = torch.empty((N, wc), dtype=torch.int32, device=self.device)
             lde = self._wrap(lde_t, N, wc)
@@ -207,19 +244,15 @@ class ShardedRunner:
         return self.prover.commit_and_fri(self.trace_t)
 
     def prepare_host(self):
-        t = self.torch.empty((self.n, self.wl), dtype=self.torch.int32, pin_memory=True)
-        t.copy_(self.trace_t)
+        self.host_t = self.prover.host_panels(self.trace_t)
         self.torch.cuda.synchronize()
-        self.host_t = t
-        self.dev_in = self.torch.empty_like(self.trace_t)
 
     def step_e2e(self):
-        self.dev_in.copy_(self.host_t, non_blocking=True)  # this rank's column shard, pinned host -> HBM
-        return self.prover.commit_and_fri(self.dev_in)
+        # this rank's column shard: pinned host panels -> HBM inside the step, overlapped with the LDE
+        return self.prover.commit_and_fri(None, host_panels=self.host_t)
 
     def release_host(self):
         self.host_t = None
-        self.dev_in = None
 
     def close(self):
         self.trace_t = None

@@ -55,6 +55,21 @@ def test_lde_fast_path(ts, ctx, orc, log_n, width, b, digits, monkeypatch):
     pc.check_lde(ts, ctx, orc, log_n, width, b)
 
 
+def test_pcs_commit_host_pipelined(ts, ctx, orc, monkeypatch):
+    """ts_pcs_commit_host cuts a wide trace into column chunks (H2D of chunk k+1 overlaps the LDE of chunk k on the
+    GPU); each chunk is an LDE window into the full-width output.  TS_CHUNK_COLS shrinks the chunk for the emulator."""
+    import numpy as np
+
+    monkeypatch.setenv("TS_CHUNK_COLS", "8")
+    ev = pc.rand_mat(21, 1 << 18, 20)  # chunks of 8, 8 and 4 columns
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
+    root, data = pcs.commit_host([(pcs.natural_domain_for_degree(1 << 18), ts.to_monty(ev))])
+    lde = orc.pcs_lde_committed(ev, 1)
+    assert np.array_equal(mm.get_matrices(data)[0].to_canonical(), lde)
+    assert root == orc.mmcs_commit([lde]).root
+
+
 def test_lde_other_shift(ts, ctx, orc):
     pc.check_lde(ts, ctx, orc, 6, 4, 2, shift=1)
     pc.check_lde(ts, ctx, orc, 12, 2, 1, shift=pow(31, 5, pc.P))

@@ -180,6 +180,22 @@ def test_pcs_commit(ts, ctx, orc):
     pc.check_pcs_commit(ts, ctx, orc, [(14, 40), (14, 4)], 2)
 
 
+@pytest.mark.parametrize("width", [192, 160])
+def test_pcs_commit_host_pipelined(ts, ctx, orc, width):
+    """ts_pcs_commit_host on a trace wide enough for the H2D/LDE pipeline (64-column chunks, last one partial)."""
+    ev = orc.splitmix_matrix(9, 1 << 18, width)
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
+    dom = pcs.natural_domain_for_degree(1 << 18)
+    root_h, data_h = pcs.commit_host([(dom, ts.to_monty(ev))])
+    root_d, _ = pcs.commit([(dom, ts.DeviceMatrix.from_canonical(ctx, ev))])
+    assert root_h == root_d
+    cols = [0, 63, 64, width - 1]
+    lde = mm.get_matrices(data_h)[0].to_canonical()
+    assert np.array_equal(lde[:, cols], orc.pcs_lde_committed(np.ascontiguousarray(ev[:, cols]), 1))
+    assert root_h == orc.mmcs_commit([orc.pcs_lde_committed(ev, 1)]).root
+
+
 def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
