@@ -204,7 +204,7 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
     ts = load_pkg()
-    ts.load_library()
+    ts.load_library(os.environ.get("TAPSTARK_LIB"))  # TAPSTARK_LIB: A/B builds of the same sources (experiments)
     # a dedicated (non-default) torch stream is handed to the library, so torch.cuda.Event timing, torch's own
     # kernels (input generation, NCCL) and the library's kernels are all ordered on ONE stream
     stream = torch.cuda.Stream()

@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__r
 // (2 p^2 < p 2^32 keeps the Montgomery reduction in range), so one reduction serves two columns.
 // apow must be padded with zeros to a multiple of 16 entries.
 constexpr int DOT_FAST_WARPS = 8;
-__global__ void __launch_bounds__(DOT_FAST_WARPS * 32) dot_rows_fast_kernel(const uint32_t *__restrict__ m, size_t rows,
+#ifndef TS_DOT_MINBLOCKS
+#define TS_DOT_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_rows_fast_kernel(const uint32_t *__restrict__ m, size_t rows,
                                                                           uint32_t width, const uint4 *__restrict__ apow,
                                                                           uint4 *__restrict__ out, int accumulate) {
     TS_DYN_SMEM(uint32_t, sm);

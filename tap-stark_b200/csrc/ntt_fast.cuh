@@ -43,6 +43,19 @@ TS_D uint2 btw(const FastTables &t, uint32_t e) {
     return __ldg(t.tw_big + e);
 }
 
+// 16-byte global load of a tile segment.  A tile row segment is only 4*K bytes (32 B for D = 11) of a row that the
+// neighbouring column-slice CTAs read next, so L2 is asked to fetch the whole 128-byte line: DRAM then sees one
+// 128 B burst instead of four scattered 32 B sector reads.
+TS_D uint4 ldg_tile(const uint32_t *p) {
+#if defined(__CUDA_ARCH__) && !defined(TS_NO_L2_128B)
+    uint4 v;
+    asm volatile("ld.global.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+
 template <int D>
 TS_D uint32_t phys(uint32_t lane, uint32_t p) {
     return (lane << D) | (ntt::swz(p) ^ ((lane & 7u) << 2));
@@ -59,6 +72,7 @@ TS_D void dif_m8(const uint32_t *src, uint32_t *dst, const FastTables &t, const 
     uint2 tw[R];
     TS_UNROLL
     for (int i = 1; i < R; i++) tw[i] = stw<INV, SM, D, 8>(t, sm_tab, g, (uint32_t)brev_c(i, LOGR), i);
+    TS_UNROLL2
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sg ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t x[R];
@@ -85,6 +99,7 @@ TS_D void dif_m4(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int t
     uint2 tw[16];
     TS_UNROLL
     for (int i = 1; i < 16; i++) tw[i] = stw<INV, SM, 8, 4>(t, sm_tab, g, (uint32_t)brev_c(i, 4), i);
+    TS_UNROLL2
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t x[16];
@@ -111,6 +126,7 @@ TS_D void dif_m0(uint32_t *tile, const uint2 (&pt)[16], int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t gq = tid & (G - 1);
     const uint32_t pb = (gq << 4) ^ (gq & 15u) ^ (((gq >> 4) & 1u) << 4);
+    TS_UNROLL2
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t x[16];
@@ -132,6 +148,7 @@ TS_D void dit_m0(uint32_t *tile, int tid) {
     constexpr int G = 1 << (D - 4), K = 1 << (14 - D);
     const uint32_t gq = tid & (G - 1);
     const uint32_t pb = (gq << 4) ^ (gq & 15u) ^ (((gq >> 4) & 1u) << 4);
+    TS_UNROLL2
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t v[16];
@@ -150,6 +167,7 @@ TS_D void dit_m4(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int t
     uint2 tw[16];  // for digit c: w_256^-(c j)
     TS_UNROLL
     for (int c = 1; c < 16; c++) tw[c] = stw<true, SM, 8, 4>(t, sm_tab, j, (uint32_t)c, c);
+    TS_UNROLL2
     for (int lane = tid >> (D - 4); lane < K; lane += (NT >> (D - 4)) > 0 ? (NT >> (D - 4)) : 1) {
         const uint32_t base = ((uint32_t)lane << D) | (pb ^ ((lane & 7u) << 2));
         uint32_t v[16];
@@ -169,6 +187,7 @@ TS_D void dit_m8(uint32_t *tile, const FastTables &t, const uint2 *sm_tab, int t
     uint2 tw[R];
     TS_UNROLL
     for (int c = 1; c < R; c++) tw[c] = stw<true, SM, D, 8>(t, sm_tab, j, (uint32_t)c, c);
+    TS_UNROLL2
     for (int lane = tid >> 8; lane < K; lane += NT / 256) {
         const uint32_t b0 = ((uint32_t)lane << D) | (sj ^ ((lane & 7u) << 2)), b1 = b0 ^ 16u;
         uint32_t v[R];
@@ -191,31 +210,26 @@ template <int D, bool BREV, int NT>
 TS_D void load_tile(uint32_t *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch,
                     uint32_t ncols, uint32_t col0, int tid) {
     constexpr int LOGV = 12 - D, NV = 1 << LOGV;  // vectors per position (K/4)
-    constexpr int TOTAL = (1 << D) * NV;
+    constexpr int TOTAL = (1 << D) * NV;          // = 4096 uint4 per tile
+    constexpr int U = TOTAL / NT;                 // every load of the tile is issued before the first use:
+    static_assert(TOTAL % NT == 0, "tile");       // ONE memory round trip per tile (profiles/r01: 4 batches of 4
+    uint4 val[U];                                 // loads made this phase 35 % of the kernel)
     TS_UNROLL
-    for (int it0 = 0; it0 < TOTAL; it0 += 4 * NT) {
-        uint4 val[4];
-        TS_UNROLL
-        for (int u = 0; u < 4; u++) {
-            const int it = it0 + u * NT + tid;
-            const uint32_t v = it & (NV - 1), q = it >> LOGV;
-            const uint32_t r = BREV ? brev_bits(q, D) : q;
-            const uint32_t col = col0 + 4 * v;
-            val[u] = (it < TOTAL && col < ncols)
-                         ? *reinterpret_cast<const uint4 *>(src + (row_base + (size_t)r * row_stride) * pitch + col)
-                         : make_uint4(0, 0, 0, 0);
-        }
-        TS_UNROLL
-        for (int u = 0; u < 4; u++) {
-            const int it = it0 + u * NT + tid;
-            if (it < TOTAL) {
-                const uint32_t v = it & (NV - 1), q = it >> LOGV;
-                tile[phys<D>(4 * v + 0, q)] = val[u].x;
-                tile[phys<D>(4 * v + 1, q)] = val[u].y;
-                tile[phys<D>(4 * v + 2, q)] = val[u].z;
-                tile[phys<D>(4 * v + 3, q)] = val[u].w;
-            }
-        }
+    for (int u = 0; u < U; u++) {
+        const int it = u * NT + tid;
+        const uint32_t v = it & (NV - 1), q = it >> LOGV;
+        const uint32_t r = BREV ? brev_bits(q, D) : q;
+        const uint32_t col = col0 + 4 * v;
+        val[u] = col < ncols ? ldg_tile(src + (row_base + (size_t)r * row_stride) * pitch + col) : make_uint4(0, 0, 0, 0);
+    }
+    TS_UNROLL
+    for (int u = 0; u < U; u++) {
+        const int it = u * NT + tid;
+        const uint32_t v = it & (NV - 1), q = it >> LOGV;
+        tile[phys<D>(4 * v + 0, q)] = val[u].x;
+        tile[phys<D>(4 * v + 1, q)] = val[u].y;
+        tile[phys<D>(4 * v + 2, q)] = val[u].z;
+        tile[phys<D>(4 * v + 3, q)] = val[u].w;
     }
 }
 template <int D, int NT>
@@ -249,11 +263,17 @@ struct FastPassParams {
     int tw_shift;  // big_log - (lo_bits + D)
     FastTables t;
 };
+#ifndef TS_PASS_MINBLOCKS
+#define TS_PASS_MINBLOCKS 2
+#endif
+#ifndef TS_MID_NT
+#define TS_MID_NT 512
+#endif
 constexpr int PASS_NT = 256;
 
 // In-place digit pass, one tile = (hi, lo) x column slice: row = (hi << (lo_bits+D)) | (q << lo_bits) | lo
 template <int D, bool INV>
-__global__ void __launch_bounds__(PASS_NT, 3) ntt_pass_fast_kernel(FastPassParams p) {
+__global__ void __launch_bounds__(PASS_NT, TS_PASS_MINBLOCKS) ntt_pass_fast_kernel(FastPassParams p) {
     TS_DYN_SMEM(uint32_t, tile);
     const int tid = threadIdx.x;
     const uint32_t cs = blockIdx.x % p.n_col_slices, tile_id = blockIdx.x / p.n_col_slices;
@@ -285,7 +305,7 @@ struct FastMidParams {
     const uint2 *pre_tab;   // [2^b][2^D]
     const uint2 *lane_tab;  // [2^b][2^klo_bits]
 };
-constexpr int MID_NT = 512;
+constexpr int MID_NT = TS_MID_NT;
 
 template <int D>
 __global__ void __launch_bounds__(MID_NT, 1) lde_mid_fast_kernel(FastMidParams p) {

@@ -12,6 +12,7 @@
 #define TS_LAUNCH(kfn, grid, block, smem, stream, ...) \
     ts_emul::launch(dim3(grid), dim3(block), (smem), [=]() { kfn(__VA_ARGS__); })
 #define TS_UNROLL
+#define TS_UNROLL2
 #else
 #include <cuda_runtime.h>
 #define TS_DYN_SMEM(type, name)                                   \
@@ -19,6 +20,11 @@
     type *name = reinterpret_cast<type *>(name##_raw_)
 #define TS_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TS_UNROLL _Pragma("unroll")
+#ifndef TS_NO_LANE_UNROLL2
+#define TS_UNROLL2 _Pragma("unroll 2")
+#else
+#define TS_UNROLL2 _Pragma("unroll 1")
+#endif
 #endif
 
 #define TS_HD __host__ __device__ __forceinline__
