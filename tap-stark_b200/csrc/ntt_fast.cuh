@@ -258,6 +258,7 @@ struct FastPassParams {
     const uint32_t *src;
     uint32_t *dst;
     uint32_t src_pitch, dst_pitch, ncols;
+    size_t src_slice = 0, dst_slice = 0;  // != 0: "blocked" layout [col / 8][row][8] with this slice stride (ntt_pm only)
     int lo_bits, hi_bits;
     uint32_t n_col_slices;
     int tw_shift;  // big_log - (lo_bits + D)
@@ -298,6 +299,7 @@ struct FastMidParams {
     const uint32_t *src;
     uint32_t *dst;
     uint32_t src_pitch, dst_pitch, ncols;
+    size_t src_slice = 0, dst_slice = 0;
     int klo_bits, b;
     uint32_t n_col_slices;
     int tw_shift;  // big_log - m

@@ -1,0 +1,611 @@
+// ntt_pm.cuh -- "position-major" digit kernels: the third and fastest NTT path (wide matrices, D in {9,10,11}).
+//
+// Same mathematics and tile shape as ntt_fast.cuh (2^D positions x 2^(14-D) lanes = 64 KiB, lanes = adjacent
+// columns), but the shared-memory tile is laid out position-major in 16-byte units:
+//
+//     unit(h, p) = (h * L) ^ s3(h) ^ sigma(p)      h = lane / 4   ("quad": 4 adjacent columns, one uint4)
+//     sigma(p)   = p ^ ((p >> 3) & 3) ^ (((p >> 5) & 1) << 2),   s3(h) = 3-bit reversal of h (staggers tile I/O)
+//
+// and a work item is (butterfly group, quad): a thread holds R positions x 4 columns in registers.  Consequences
+// (profiles/r01: in ntt_fast tile I/O took 56 % of the time with 31 % of the instructions, and the rounds stalled
+// on the shared-memory instruction queue):
+//   * every shared access is LDS.128 / STS.128, every global access LDG.128 / STG.128 straight to/from the tile
+//     (0.5 instr per element for I/O instead of ~8), twiddles are fetched once per 4 columns;
+//   * rounds are radix 8 (R positions x 4 columns = 32 data registers): 2^D = 2^(D-8) * 8 * 8 * 4;
+//   * sigma makes all four round shapes (strides 256, 32, 4, 1) and the tile I/O conflict free at 16-byte
+//     granularity, and element addresses are  base + const  or  base ^ const.
+#pragma once
+#include "ntt_fast.cuh"
+
+namespace nttp {
+
+using ntt::brev_bits;
+using ntt::brev_c;
+using nttf::btw;
+using nttf::FastTables;
+
+TS_D uint32_t sigma(uint32_t p) { return p ^ ((p >> 3) & 3u) ^ (((p >> 5) & 1u) << 2); }
+// quad offset: everything below combines with XOR only (or adds constants into zero bit fields), so element
+// addresses are  hx ^ const  /  hx' + const
+template <int D>
+TS_D uint32_t hx(uint32_t h) {
+    return (h << D) ^ (((h & 1u) << 2) | (h & 2u) | ((h >> 2) & 1u));
+}
+
+// 4-wide field helpers (one uint4 = the same position in 4 adjacent columns)
+struct V4 {
+    uint32_t v[4];
+};
+TS_D V4 ld4(const uint4 *p) {
+    const uint4 t = *p;
+    return V4{{t.x, t.y, t.z, t.w}};
+}
+TS_D void st4(uint4 *p, const V4 &a) { *p = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+TS_D V4 vadd(const V4 &a, const V4 &b) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = bb::add(a.v[k], b.v[k]);
+    return r;
+}
+TS_D V4 vsub(const V4 &a, const V4 &b) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = bb::sub(a.v[k], b.v[k]);
+    return r;
+}
+// (a - b) * w, w a Shoup pair
+TS_D V4 vsubmul(const V4 &a, const V4 &b, uint32_t w, uint32_t wp) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = bb::shoup(a.v[k] - b.v[k] + bb::P, w, wp);
+    return r;
+}
+TS_D V4 vmul(const V4 &a, uint2 w) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = bb::shoup(a.v[k], w.x, w.y);
+    return r;
+}
+TS_D V4 vmul2(const V4 &a, uint2 w1, uint2 w2) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = bb::shoup(bb::shoup_lazy(a.v[k], w1.x, w1.y), w2.x, w2.y);
+    return r;
+}
+
+// radix-2^LOGR DIF DFT on R quads, compile-time twiddles; natural in, register i holds frequency brev(i)
+template <int LOGR, bool INV>
+TS_D void dft_v4(V4 (&x)[1 << LOGR]) {
+    constexpr bb::InnerTw<LOGR, INV> T{};
+    constexpr int R = 1 << LOGR;
+    TS_UNROLL
+    for (int s = 0; s < LOGR; s++) {
+        const int half = R >> (s + 1);
+        TS_UNROLL
+        for (int blk = 0; blk < R; blk += 2 * half) {
+            TS_UNROLL
+            for (int j = 0; j < half; j++) {
+                const V4 a = x[blk + j], b = x[blk + j + half];
+                x[blk + j] = vadd(a, b);
+                const int e = j << s;
+                x[blk + j + half] = e == 0 ? vsub(a, b) : vsubmul(a, b, T.w[e], T.wp[e]);
+            }
+        }
+    }
+}
+
+// inter-round twiddle of register i for group g: global power table, or a shared [i][g] table (lde_mid)
+template <bool INV, bool SM, int LOGS, int LOGG>
+TS_D uint2 rtw(const FastTables &t, const uint2 *sm_tab, uint32_t g, uint32_t u, uint32_t i) {
+    if (SM) return sm_tab[(i << LOGG) + g];
+    return __ldg((INV ? t.tw_small_inv : t.tw_small) + ((g * u) << (t.small_log - LOGS)));
+}
+
+template <int D>
+struct Geo {
+    static constexpr int L = 1 << D;
+    static constexpr int K = 1 << (14 - D);       // lanes (columns) per tile
+    static constexpr int NQ = K / 4;              // quads per position
+    static constexpr int UNITS = NQ * L;          // 16-byte units per tile (64 KiB)
+    static constexpr int LOGR1 = D - 8;           // first-round radix (2, 4 or 8)
+};
+
+// ---- DIF rounds (forward direction of the data flow; INV only selects the roots) ---------------------------
+// R1: radix 2^(D-8), stride 256.  PRE (lde_mid): position c of the item is multiplied by pw[c] and by `lw`.
+template <int D, bool INV, bool PRE, bool SM, int NT>
+TS_D void dif_r1(const uint4 *src, uint4 *dst, const FastTables &t, const uint2 *sm_tab, const uint2 *pre_tab, uint2 lw,
+                 int tid) {
+    using G = Geo<D>;
+    constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
+    for (int item = tid; item < 256 * G::NQ; item += NT) {
+        const uint32_t g = item & 255, h = item >> 8;
+        const uint32_t b0 = hx<D>(h) ^ sigma(g);  // sigma(g + 256 c) = sigma(g) + 256 c
+        V4 x[R];
+        TS_UNROLL
+        for (int c = 0; c < R; c++) x[c] = ld4(src + b0 + 256 * c);
+        if (PRE) {
+            TS_UNROLL
+            for (int c = 0; c < R; c++) x[c] = vmul2(x[c], __ldg(pre_tab + g + 256 * c), lw);
+        }
+        dft_v4<LOGR, INV>(x);
+        TS_UNROLL
+        for (int i = 1; i < R; i++) x[i] = vmul(x[i], rtw<INV, SM, D, 8>(t, sm_tab, g, (uint32_t)brev_c(i, LOGR), i));
+        TS_UNROLL
+        for (int c = 0; c < R; c++) st4(dst + b0 + 256 * c, x[c]);
+    }
+}
+// R2: radix 8 inside blocks of 256, stride 32: p = 256 blk + g + 32 c
+template <int D, bool INV, bool SM, int NT>
+TS_D void dif_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 8) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
+        const uint32_t blk = grp >> 5, g = grp & 31;
+        const uint32_t b0 = hx<D>(h) ^ ((blk << 8) | (g ^ ((g >> 3) & 3u))), b1 = b0 ^ 4u;  // bit 2 ^= c & 1
+        V4 x[8];
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) x[c] = ld4(tile + ((c & 1) ? b1 : b0) + 32 * c);
+        dft_v4<3, INV>(x);
+        TS_UNROLL
+        for (int i = 1; i < 8; i++) x[i] = vmul(x[i], rtw<INV, SM, 8, 5>(t, sm_tab, g, (uint32_t)brev_c(i, 3), i));
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) st4(tile + ((c & 1) ? b1 : b0) + 32 * c, x[c]);
+    }
+}
+// R3: radix 8 inside blocks of 32, stride 4: p = 32 blk + g + 4 c
+template <int D, bool INV, bool SM, int NT>
+TS_D void dif_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 8) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
+        const uint32_t blk = grp >> 2, g = grp & 3;
+        const uint32_t base = hx<D>(h) ^ ((blk << 5) | g) ^ ((blk & 1u) << 2);
+        V4 x[8];
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) x[c] = ld4(tile + (base ^ (uint32_t)((4 * c) ^ ((c >> 1) & 3))));
+        dft_v4<3, INV>(x);
+        TS_UNROLL
+        for (int i = 1; i < 8; i++) x[i] = vmul(x[i], rtw<INV, SM, 5, 2>(t, sm_tab, g, (uint32_t)brev_c(i, 3), i));
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) st4(tile + (base ^ (uint32_t)((4 * c) ^ ((c >> 1) & 3))), x[c]);
+    }
+}
+// R4: radix 4 on consecutive positions p = 4 blk + c.  POST: inter-digit twiddle w^(+-lo*brev_D(p)) per position.
+template <int D, bool INV, bool POST, int NT>
+TS_D void dif_r4(uint4 *tile, const FastTables &t, uint32_t lo, int tw_shift, int tid) {
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 4) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t blk = item & (G::L / 4 - 1), h = item / (G::L / 4);
+        const uint32_t base = hx<D>(h) ^ (blk << 2) ^ ((blk >> 1) & 3u) ^ (((blk >> 3) & 1u) << 2);
+        uint2 pt[4];
+        if (POST) {
+            TS_UNROLL
+            for (int c = 0; c < 4; c++) pt[c] = btw<INV>(t, (lo * brev_bits(4 * blk + c, D)) << tw_shift);
+        }
+        V4 x[4];
+        TS_UNROLL
+        for (int c = 0; c < 4; c++) x[c] = ld4(tile + (base ^ (uint32_t)c));
+        dft_v4<2, INV>(x);
+        if (POST) {
+            TS_UNROLL
+            for (int c = 0; c < 4; c++) x[c] = vmul(x[c], pt[c]);
+        }
+        TS_UNROLL
+        for (int c = 0; c < 4; c++) st4(tile + (base ^ (uint32_t)c), x[c]);
+    }
+}
+
+// ---- DIT rounds (inverse sub-transform of lde_mid: bit-reversed positions in, natural out) ------------------
+// block i of a round holds the sub-sequence with digit brev(i); digit c is multiplied by w^-(c j) before the DFT.
+template <int D, int NT>
+TS_D void dit_r4(uint4 *tile, int tid) {  // radix 4, consecutive positions, no twiddles
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 4) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t blk = item & (G::L / 4 - 1), h = item / (G::L / 4);
+        const uint32_t base = hx<D>(h) ^ (blk << 2) ^ ((blk >> 1) & 3u) ^ (((blk >> 3) & 1u) << 2);
+        V4 v[4];
+        TS_UNROLL
+        for (int c = 0; c < 4; c++) v[c] = ld4(tile + (base ^ (uint32_t)brev_c(c, 2)));
+        dft_v4<2, true>(v);
+        TS_UNROLL
+        for (int u = 0; u < 4; u++) st4(tile + (base ^ (uint32_t)u), v[brev_c(u, 2)]);
+    }
+}
+template <int D, bool SM, int NT>
+TS_D void dit_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 8, stride 4
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 8) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
+        const uint32_t blk = grp >> 2, j = grp & 3;
+        const uint32_t base = hx<D>(h) ^ ((blk << 5) | j) ^ ((blk & 1u) << 2);
+        V4 v[8];
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) {
+            const int i = brev_c(c, 3);
+            v[c] = ld4(tile + (base ^ (uint32_t)((4 * i) ^ ((i >> 1) & 3))));
+        }
+        TS_UNROLL
+        for (int c = 1; c < 8; c++) v[c] = vmul(v[c], rtw<true, SM, 5, 2>(t, sm_tab, j, (uint32_t)c, c));
+        dft_v4<3, true>(v);
+        TS_UNROLL
+        for (int u = 0; u < 8; u++) st4(tile + (base ^ (uint32_t)((4 * u) ^ ((u >> 1) & 3))), v[brev_c(u, 3)]);
+    }
+}
+template <int D, bool SM, int NT>
+TS_D void dit_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 8, stride 32
+    using G = Geo<D>;
+    constexpr int ITEMS = (G::L / 8) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
+        const uint32_t blk = grp >> 5, j = grp & 31;
+        const uint32_t b0 = hx<D>(h) ^ ((blk << 8) | (j ^ ((j >> 3) & 3u))), b1 = b0 ^ 4u;
+        V4 v[8];
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) {
+            const int i = brev_c(c, 3);
+            v[c] = ld4(tile + ((i & 1) ? b1 : b0) + 32 * i);
+        }
+        TS_UNROLL
+        for (int c = 1; c < 8; c++) v[c] = vmul(v[c], rtw<true, SM, 8, 5>(t, sm_tab, j, (uint32_t)c, c));
+        dft_v4<3, true>(v);
+        TS_UNROLL
+        for (int u = 0; u < 8; u++) st4(tile + ((u & 1) ? b1 : b0) + 32 * u, v[brev_c(u, 3)]);
+    }
+}
+template <int D, bool SM, int NT>
+TS_D void dit_r1(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 2^(D-8), stride 256
+    using G = Geo<D>;
+    constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
+    for (int item = tid; item < 256 * G::NQ; item += NT) {
+        const uint32_t j = item & 255, h = item >> 8;
+        const uint32_t b0 = hx<D>(h) ^ sigma(j);
+        V4 v[R];
+        TS_UNROLL
+        for (int c = 0; c < R; c++) v[c] = ld4(tile + b0 + 256 * brev_c(c, LOGR));
+        TS_UNROLL
+        for (int c = 1; c < R; c++) v[c] = vmul(v[c], rtw<true, SM, D, 8>(t, sm_tab, j, (uint32_t)c, c));
+        dft_v4<LOGR, true>(v);
+        TS_UNROLL
+        for (int u = 0; u < R; u++) st4(tile + b0 + 256 * u, v[brev_c(u, LOGR)]);
+    }
+}
+
+// ---- tile I/O: one uint4 per (position, quad), straight between global memory and the tile -----------------
+// Matrix layouts.  slice == 0: row-major, word (row, col) at row * pitch + col.  slice != 0: "blocked" internal
+// layout [col / 8][row][8 columns] with `slice` words between column groups.  profiles/tools/tile_copy.cu: with
+// row-major intermediates the strided digit steps 2 MiB between its 32-byte segments (one TLB page each,
+// 2.0 TB/s); blocked intermediates step 64 KiB (3.7 TB/s) and make the contiguous digit's tile a single 64 KiB run
+// (6.7 TB/s).  Only the first read and the last write of an LDE touch the caller's row-major matrices.
+TS_D size_t word_off(size_t row, uint32_t col, uint32_t pitch, size_t slice) {
+    return slice ? (size_t)(col >> 3) * slice + row * 8 + (col & 7u) : row * pitch + col;
+}
+
+// BREV: tile position q receives source row brev_D(q)
+template <int D, bool BREV, int NT>
+TS_D void load_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                    uint32_t ncols, uint32_t col0, int tid) {
+    using G = Geo<D>;
+    constexpr int TOTAL = G::L * G::NQ, U = TOTAL / NT;
+    static_assert(TOTAL % NT == 0, "tile");
+    uint4 val[U];
+    TS_UNROLL
+    for (int u = 0; u < U; u++) {
+        const int it = u * NT + tid;
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        const uint32_t r = BREV ? brev_bits(q, D) : q;
+        const uint32_t col = col0 + 4 * h;
+        val[u] = col < ncols ? nttf::ldg_tile(src + word_off(row_base + (size_t)r * row_stride, col, pitch, slice))
+                             : make_uint4(0, 0, 0, 0);
+    }
+    TS_UNROLL
+    for (int u = 0; u < U; u++) {
+        const int it = u * NT + tid;
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        tile[hx<D>(h) ^ sigma(q)] = val[u];
+    }
+}
+template <int D, int NT>
+TS_D void store_tile(const uint4 *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                     uint32_t ncols, uint32_t col0, int tid) {
+    using G = Geo<D>;
+    constexpr int TOTAL = G::L * G::NQ;
+    for (int it = tid; it < TOTAL; it += NT) {
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        const uint32_t col = col0 + 4 * h;
+        if (col < ncols)
+            *reinterpret_cast<uint4 *>(dst + word_off(row_base + (size_t)q * row_stride, col, pitch, slice)) =
+                tile[hx<D>(h) ^ sigma(q)];
+    }
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------
+#ifndef TS_PM_PASS_MINBLOCKS
+#define TS_PM_PASS_MINBLOCKS 2
+#endif
+constexpr int PM_PASS_NT = 256;
+
+template <int D, bool INV>
+__global__ void __launch_bounds__(PM_PASS_NT, TS_PM_PASS_MINBLOCKS) ntt_pass_pm_kernel(nttf::FastPassParams p) {
+    TS_DYN_SMEM(uint4, tile);
+    const int tid = threadIdx.x;
+    const uint32_t cs = blockIdx.x % p.n_col_slices, tile_id = blockIdx.x / p.n_col_slices;
+    const uint32_t lo = tile_id & ((1u << p.lo_bits) - 1), hi = tile_id >> p.lo_bits;
+    const uint32_t col0 = cs << (14 - D);
+    const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo, row_stride = (size_t)1 << p.lo_bits;
+    load_tile<D, false, PM_PASS_NT>(tile, p.src, row_base, row_stride, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    __syncthreads();
+    dif_r1<D, INV, false, false, PM_PASS_NT>(tile, tile, p.t, nullptr, nullptr, make_uint2(0, 0), tid);
+    __syncthreads();
+    dif_r2<D, INV, false, PM_PASS_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    dif_r3<D, INV, false, PM_PASS_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    if (p.lo_bits > 0) dif_r4<D, INV, true, PM_PASS_NT>(tile, p.t, lo, p.tw_shift, tid);
+    else dif_r4<D, INV, false, PM_PASS_NT>(tile, p.t, 0, 0, tid);
+    __syncthreads();
+    store_tile<D, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
+}
+
+#ifndef TS_PM_MID_NT
+#define TS_PM_MID_NT 512
+#endif
+constexpr int PM_MID_NT = TS_PM_MID_NT;
+
+template <int D>
+__global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidParams p) {
+    TS_DYN_SMEM(uint4, smem);
+    using G = Geo<D>;
+    constexpr int R1 = 1 << G::LOGR1;
+    uint4 *A = smem, *W = smem + G::UNITS;
+    // shared inter-round twiddle tables [register i][group g] (conflict-free LDS, see nttf::stw)
+    uint2 *f1 = reinterpret_cast<uint2 *>(W + G::UNITS);  // fwd R1: w_L^(g brev(i)),    R1 x 256
+    uint2 *f2 = f1 + R1 * 256;                            // fwd R2: w_256^(g brev3(i)), 8 x 32
+    uint2 *f3 = f2 + 256;                                 // fwd R3: w_32^(g brev3(i)),  8 x 4
+    uint2 *i1 = f3 + 32;                                  // inv (DIT) tables: w^-(c j)
+    uint2 *i2 = i1 + R1 * 256;
+    uint2 *i3 = i2 + 256;
+    const int tid = threadIdx.x;
+    const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = blockIdx.x / p.n_col_slices;
+    const uint32_t col0 = cs << (14 - D);
+    const int m = D + p.klo_bits;
+    const FastTables &t = p.t;
+    for (int e = tid; e < R1 * 256; e += PM_MID_NT) {
+        const uint32_t i = e >> 8, g = e & 255;
+        f1[e] = __ldg(t.tw_small + ((g * brev_bits(i, G::LOGR1)) << (t.small_log - D)));
+        i1[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - D)));
+    }
+    for (int e = tid; e < 256; e += PM_MID_NT) {
+        const uint32_t i = e >> 5, g = e & 31;
+        f2[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 8)));
+        i2[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 8)));
+    }
+    for (int e = tid; e < 32; e += PM_MID_NT) {
+        const uint32_t i = e >> 2, g = e & 3;
+        f3[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 5)));
+        i3[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 5)));
+    }
+    // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
+    load_tile<D, true, PM_MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    __syncthreads();
+    dit_r4<D, PM_MID_NT>(A, tid);
+    __syncthreads();
+    dit_r3<D, true, PM_MID_NT>(A, t, i3, tid);
+    __syncthreads();
+    dit_r2<D, true, PM_MID_NT>(A, t, i2, tid);
+    __syncthreads();
+    dit_r1<D, true, PM_MID_NT>(A, t, i1, tid);
+    for (uint32_t j = 0; j < (1u << p.b); j++) {
+        const uint2 lw = __ldg(p.lane_tab + ((size_t)j << p.klo_bits) + Kc);
+        __syncthreads();  // orders the last DIT round / the previous coset's store before W is rewritten
+        dif_r1<D, false, true, true, PM_MID_NT>(A, W, t, f1, p.pre_tab + ((size_t)j << D), lw, tid);
+        __syncthreads();
+        dif_r2<D, false, true, PM_MID_NT>(W, t, f2, tid);
+        __syncthreads();
+        dif_r3<D, false, true, PM_MID_NT>(W, t, f3, tid);
+        __syncthreads();
+        if (p.klo_bits > 0) dif_r4<D, false, true, PM_MID_NT>(W, t, Kc, p.tw_shift, tid);
+        else dif_r4<D, false, false, PM_MID_NT>(W, t, 0, 0, tid);
+        __syncthreads();
+        store_tile<D, PM_MID_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
+                                 p.dst_slice, p.ncols, col0, tid);
+    }
+}
+
+}  // namespace nttp
+
+// =====================================================================================================================
+// Persistent, software-pipelined variants.  profiles/tools/tile_copy.cu measured the memory-system ceiling of
+// the 2048 x 32-byte tile pattern at 4.0 TB/s (contiguous rows) and 2.0 TB/s (rows 2 MiB apart): the digit passes
+// are within 2x of their memory floor, so the remaining lever is to run memory and arithmetic CONCURRENTLY inside
+// one CTA instead of relying on 2-3 co-resident CTAs drifting out of phase: one CTA per SM loops over tiles,
+// cp.async (LDGSTS, 16 B, straight into the position-major tile) prefetches tile i+1 while tile i is transformed,
+// and the STG.128 of tile i drain while tile i+1 is transformed.
+namespace nttp {
+
+TS_D void cp_async16(uint4 *smem_dst, const uint32_t *gsrc, bool valid) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;  // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+#else
+    *smem_dst = valid ? *reinterpret_cast<const uint4 *>(gsrc) : make_uint4(0, 0, 0, 0);
+#endif
+}
+TS_D void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+TS_D void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+template <int D, bool BREV, int NT>
+TS_D void prefetch_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                        uint32_t ncols, uint32_t col0, int tid) {
+    using G = Geo<D>;
+    constexpr int TOTAL = G::L * G::NQ;
+    TS_UNROLL
+    for (int u = 0; u < TOTAL / NT; u++) {
+        const int it = u * NT + tid;
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        const uint32_t r = BREV ? brev_bits(q, D) : q;
+        const uint32_t col = col0 + 4 * h;
+        const bool ok = col < ncols;
+        cp_async16(tile + (hx<D>(h) ^ sigma(q)), src + word_off(row_base + (size_t)r * row_stride, ok ? col : 0, pitch, slice), ok);
+    }
+    cp_async_commit();
+}
+
+#ifndef TS_PM2_NT
+#define TS_PM2_NT 512
+#endif
+constexpr int PM2_NT = TS_PM2_NT;
+
+struct PersistPassParams {
+    nttf::FastPassParams p;
+    uint32_t n_tiles;  // (2^(hi_bits + lo_bits)) * n_col_slices
+};
+
+template <int D, bool INV>
+__global__ void __launch_bounds__(PM2_NT, 1) ntt_pass_pm2_kernel(PersistPassParams pp) {
+    TS_DYN_SMEM(uint4, smem);
+    using G = Geo<D>;
+    const nttf::FastPassParams &p = pp.p;
+    const int tid = threadIdx.x;
+    auto buf = [&](int i) { return smem + (i ? G::UNITS : 0); };
+    auto geom = [&](uint32_t t, uint32_t &lo, uint32_t &col0, size_t &row_base) {
+        const uint32_t cs = t % p.n_col_slices, tile_id = t / p.n_col_slices;
+        lo = tile_id & ((1u << p.lo_bits) - 1);
+        const uint32_t hi = tile_id >> p.lo_bits;
+        col0 = cs << (14 - D);
+        row_base = ((size_t)hi << (p.lo_bits + D)) + lo;
+    };
+    const size_t row_stride = (size_t)1 << p.lo_bits;
+    uint32_t t = blockIdx.x, lo, col0;
+    size_t row_base;
+    int cur = 0;
+    if (t < pp.n_tiles) {
+        geom(t, lo, col0, row_base);
+        prefetch_tile<D, false, PM2_NT>(buf(0), p.src, row_base, row_stride, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    }
+    for (; t < pp.n_tiles; t += gridDim.x) {
+        geom(t, lo, col0, row_base);
+        const uint32_t tn = t + gridDim.x;
+        if (tn < pp.n_tiles) {
+            uint32_t lo2, col2;
+            size_t rb2;
+            geom(tn, lo2, col2, rb2);
+            prefetch_tile<D, false, PM2_NT>(buf(cur ^ 1), p.src, rb2, row_stride, p.src_pitch, p.src_slice, p.ncols, col2, tid);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        uint4 *tile = buf(cur);
+        dif_r1<D, INV, false, false, PM2_NT>(tile, tile, p.t, nullptr, nullptr, make_uint2(0, 0), tid);
+        __syncthreads();
+        dif_r2<D, INV, false, PM2_NT>(tile, p.t, nullptr, tid);
+        __syncthreads();
+        dif_r3<D, INV, false, PM2_NT>(tile, p.t, nullptr, tid);
+        __syncthreads();
+        if (p.lo_bits > 0) dif_r4<D, INV, true, PM2_NT>(tile, p.t, lo, p.tw_shift, tid);
+        else dif_r4<D, INV, false, PM2_NT>(tile, p.t, 0, 0, tid);
+        __syncthreads();
+        store_tile<D, PM2_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
+        __syncthreads();  // buf[cur] is the prefetch target of the next iteration
+        cur ^= 1;
+    }
+}
+
+struct PersistMidParams {
+    nttf::FastMidParams p;
+    uint32_t n_tiles;  // 2^klo_bits * n_col_slices
+};
+
+template <int D>
+__global__ void __launch_bounds__(PM2_NT, 1) lde_mid_pm2_kernel(PersistMidParams pp) {
+    TS_DYN_SMEM(uint4, smem);
+    using G = Geo<D>;
+    constexpr int R1 = 1 << G::LOGR1;
+    const nttf::FastMidParams &p = pp.p;
+    uint4 *W = smem;                                   // work tile of the current coset
+    auto Abuf = [&](int i) { return smem + (i ? 2 * G::UNITS : G::UNITS); };  // coefficient tile / prefetch target
+    uint2 *f1 = reinterpret_cast<uint2 *>(smem + 3 * G::UNITS);  // fwd R1 [i][g], R1 x 256
+    uint2 *f2 = f1 + R1 * 256;                                   // fwd R2, 8 x 32
+    uint2 *f3 = f2 + 256;                                        // fwd R3, 8 x 4
+    uint2 *i2 = f3 + 32;                                         // inverse (DIT) R2 / R3; DIT R1 reads global
+    uint2 *i3 = i2 + 256;
+    const int tid = threadIdx.x;
+    const FastTables &t = p.t;
+    for (int e = tid; e < R1 * 256; e += PM2_NT) {
+        const uint32_t i = e >> 8, g = e & 255;
+        f1[e] = __ldg(t.tw_small + ((g * brev_bits(i, G::LOGR1)) << (t.small_log - D)));
+    }
+    for (int e = tid; e < 256; e += PM2_NT) {
+        const uint32_t i = e >> 5, g = e & 31;
+        f2[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 8)));
+        i2[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 8)));
+    }
+    for (int e = tid; e < 32; e += PM2_NT) {
+        const uint32_t i = e >> 2, g = e & 3;
+        f3[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 5)));
+        i3[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 5)));
+    }
+    const int m = D + p.klo_bits;
+    uint32_t tl = blockIdx.x;
+    int cur = 0;
+    if (tl < pp.n_tiles) {
+        const uint32_t cs = tl % p.n_col_slices, Kc = tl / p.n_col_slices;
+        prefetch_tile<D, true, PM2_NT>(Abuf(0), p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.src_pitch, p.src_slice,
+                                       p.ncols, cs << (14 - D), tid);
+    }
+    for (; tl < pp.n_tiles; tl += gridDim.x) {
+        const uint32_t cs = tl % p.n_col_slices, Kc = tl / p.n_col_slices, col0 = cs << (14 - D);
+        const uint32_t tn = tl + gridDim.x;
+        if (tn < pp.n_tiles) {
+            const uint32_t cs2 = tn % p.n_col_slices, K2 = tn / p.n_col_slices;
+            prefetch_tile<D, true, PM2_NT>(Abuf(cur ^ 1), p.src, (size_t)brev_bits(K2, p.klo_bits) << D, 1, p.src_pitch,
+                                           p.src_slice, p.ncols, cs2 << (14 - D), tid);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        uint4 *A = Abuf(cur);
+        dit_r4<D, PM2_NT>(A, tid);
+        __syncthreads();
+        dit_r3<D, true, PM2_NT>(A, t, i3, tid);
+        __syncthreads();
+        dit_r2<D, true, PM2_NT>(A, t, i2, tid);
+        __syncthreads();
+        dit_r1<D, false, PM2_NT>(A, t, nullptr, tid);
+        for (uint32_t j = 0; j < (1u << p.b); j++) {
+            const uint2 lw = __ldg(p.lane_tab + ((size_t)j << p.klo_bits) + Kc);
+            __syncthreads();
+            dif_r1<D, false, true, true, PM2_NT>(A, W, t, f1, p.pre_tab + ((size_t)j << D), lw, tid);
+            __syncthreads();
+            dif_r2<D, false, true, PM2_NT>(W, t, f2, tid);
+            __syncthreads();
+            dif_r3<D, false, true, PM2_NT>(W, t, f3, tid);
+            __syncthreads();
+            if (p.klo_bits > 0) dif_r4<D, false, true, PM2_NT>(W, t, Kc, p.tw_shift, tid);
+            else dif_r4<D, false, false, PM2_NT>(W, t, 0, 0, tid);
+            __syncthreads();
+            store_tile<D, PM2_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
+                                  p.dst_slice, p.ncols, col0, tid);
+        }
+        __syncthreads();  // Abuf[cur] becomes the prefetch target two iterations from now; W is rewritten next
+        cur ^= 1;
+    }
+}
+
+}  // namespace nttp

@@ -17,6 +17,7 @@
 #include "host_side.h"
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
+#include "ntt_pm.cuh"
 
 // ------------------------------------------------------------------------------------------------ structs
 struct ts_matrix {
@@ -251,10 +252,42 @@ bool fast_shape(int d, size_t w) {
     static const bool off = getenv("TS_NO_FAST") != nullptr;
     return !off && d >= 9 && d <= 11 && w >= 8 && (w & 3) == 0;
 }
+bool use_pm() {
+    static const bool off = getenv("TS_NO_PM") != nullptr;
+    return !off;
+}
+bool use_persistent() {  // measured slower than 2 independent CTAs per SM (profiles/r01/README.md); opt-in
+    static const bool on = getenv("TS_PERSIST") != nullptr;
+    return on;
+}
 template <int D>
 int launch_pass_fast(ts_ctx *c, bool inverse, const nttf::FastPassParams &p, size_t blocks) {
     const size_t smem = (size_t)16384 * 4;
     KScope ks(c, TS_K_NTT_PASS);
+    if (use_pm() && use_persistent()) {
+        nttp::PersistPassParams pp;
+        pp.p = p;
+        pp.n_tiles = (uint32_t)blocks;
+        const unsigned grid = (unsigned)std::min<size_t>(blocks, (size_t)c->num_sms);
+        if (inverse) {
+            auto kfn = nttp::ntt_pass_pm2_kernel<D, true>;
+            TS_LAUNCH(kfn, grid, nttp::PM2_NT, 2 * smem, c->stream, pp);
+        } else {
+            auto kfn = nttp::ntt_pass_pm2_kernel<D, false>;
+            TS_LAUNCH(kfn, grid, nttp::PM2_NT, 2 * smem, c->stream, pp);
+        }
+        return check_launch(c, "ntt_pass_pm2_kernel");
+    }
+    if (use_pm()) {
+        if (inverse) {
+            auto kfn = nttp::ntt_pass_pm_kernel<D, true>;
+            TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_PASS_NT, smem, c->stream, p);
+        } else {
+            auto kfn = nttp::ntt_pass_pm_kernel<D, false>;
+            TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_PASS_NT, smem, c->stream, p);
+        }
+        return check_launch(c, "ntt_pass_pm_kernel");
+    }
     if (inverse) {
         auto kfn = nttf::ntt_pass_fast_kernel<D, true>;
         TS_LAUNCH(kfn, (unsigned)blocks, nttf::PASS_NT, smem, c->stream, p);
@@ -268,15 +301,20 @@ int launch_pass_fast(ts_ctx *c, bool inverse, const nttf::FastPassParams &p, siz
 // w columns are transformed; src_pitch/dst_pitch (0 = w) are the row strides when src/dst are column windows of
 // wider matrices (fast path only)
 int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, size_t w, int d, int lo_bits,
-                int hi_bits, bool has_scale, uint2 scale, size_t src_pitch = 0, size_t dst_pitch = 0) {
+                int hi_bits, bool has_scale, uint2 scale, size_t src_pitch = 0, size_t dst_pitch = 0,
+                size_t src_slice = 0, size_t dst_slice = 0) {
     if (!src_pitch) src_pitch = w;
     if (!dst_pitch) dst_pitch = w;
+    if ((src_slice || dst_slice) && !(use_pm() && !has_scale && fast_shape(d, w)))
+        TS_FAIL(c, TS_ERR_ARG, "blocked layouts need the position-major NTT path");
     if (!has_scale && fast_shape(d, w)) {
         nttf::FastPassParams fp;
         fp.src = src;
         fp.dst = dst;
         fp.src_pitch = (uint32_t)src_pitch;
         fp.dst_pitch = (uint32_t)dst_pitch;
+        fp.src_slice = src_slice;
+        fp.dst_slice = dst_slice;
         fp.ncols = (uint32_t)w;
         fp.lo_bits = lo_bits;
         fp.hi_bits = hi_bits;
@@ -422,27 +460,38 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
     const size_t D = dg.size();
     const int dK = dg[D - 1];
     const int klo = m - dK;
+    // Blocked intermediates ([col/8][row][8], see ntt_pm.cuh word_off): only the first read and the last write
+    // of a multi-digit LDE use the caller's row-major matrices.
+    const bool blocked = D > 1 && use_pm() && all_digits_fast(m, w) && getenv("TS_NO_BLOCKED") == nullptr;
+    const size_t w8 = (w + 7) & ~(size_t)7, N = n << b;
+    const size_t s_slice = blocked ? n * 8 : 0, i_slice = blocked ? N * 8 : 0;
+    uint32_t *inter = nullptr;  // blocked N x w intermediate between lde_mid and the last forward pass
     if (D > 1) {
         TS_TRY(ensure_big(c, m));
-        TS_TRY(ensure_scratch(c, n * w));
+        TS_TRY(ensure_scratch(c, n * (blocked ? w8 : w)));
     }
+    if (blocked) TS_CUDA(c, pool_alloc(c, (void **)&inter, N * w8 * 4));
     uint2 *pre, *lane;
-    TS_TRY(get_coset_tables(c, m, (int)b, dK, shift_monty, &pre, &lane));
+    int rc = get_coset_tables(c, m, (int)b, dK, shift_monty, &pre, &lane);
     // inverse passes over the top digits
     int used = 0;
-    for (size_t i = 0; i + 1 < D; i++) {
+    for (size_t i = 0; i + 1 < D && rc == TS_OK; i++) {
         const int lo_bits = m - used - dg[i];
-        TS_TRY(launch_pass(c, true, i == 0 ? src : c->scratch, c->scratch, w, dg[i], lo_bits, used, false,
-                           make_uint2(0, 0), i == 0 ? src_pitch : w, w));
+        rc = launch_pass(c, true, i == 0 ? src : c->scratch, c->scratch, w, dg[i], lo_bits, used, false, make_uint2(0, 0),
+                         i == 0 ? src_pitch : w, w, i == 0 ? 0 : s_slice, s_slice);
         used += dg[i];
     }
     // middle kernel
-    if (fast_shape(dK, w)) {
+    uint32_t *mid_dst = blocked ? inter : dst;
+    if (rc != TS_OK) {
+    } else if (fast_shape(dK, w)) {
         nttf::FastMidParams fp;
         fp.src = D > 1 ? c->scratch : src;
-        fp.dst = dst;
+        fp.dst = mid_dst;
         fp.src_pitch = (uint32_t)(D > 1 ? w : src_pitch);
         fp.dst_pitch = (uint32_t)dst_pitch;
+        fp.src_slice = D > 1 ? s_slice : 0;
+        fp.dst_slice = i_slice;
         fp.ncols = (uint32_t)w;
         fp.klo_bits = klo;
         fp.b = (int)b;
@@ -453,9 +502,36 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         fp.pre_tab = pre;
         fp.lane_tab = lane;
         const size_t blocks = ((size_t)1 << klo) * fp.n_col_slices;
-        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + 512 + K) * sizeof(uint2);
+        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + 1024 + K) * sizeof(uint2);
         KScope ks(c, TS_K_LDE_MID);
-        if (dK == 9) {
+        if (use_pm() && use_persistent()) {
+            nttp::PersistMidParams pp;
+            pp.p = fp;
+            pp.n_tiles = (uint32_t)blocks;
+            const unsigned grid = (unsigned)std::min<size_t>(blocks, (size_t)c->num_sms);
+            const size_t smem2 = (size_t)3 * 16384 * 4 + (((size_t)1 << dK) + 1024) * sizeof(uint2);
+            if (dK == 9) {
+                auto kfn = nttp::lde_mid_pm2_kernel<9>;
+                TS_LAUNCH(kfn, grid, nttp::PM2_NT, smem2, c->stream, pp);
+            } else if (dK == 10) {
+                auto kfn = nttp::lde_mid_pm2_kernel<10>;
+                TS_LAUNCH(kfn, grid, nttp::PM2_NT, smem2, c->stream, pp);
+            } else {
+                auto kfn = nttp::lde_mid_pm2_kernel<11>;
+                TS_LAUNCH(kfn, grid, nttp::PM2_NT, smem2, c->stream, pp);
+            }
+        } else if (use_pm()) {
+            if (dK == 9) {
+                auto kfn = nttp::lde_mid_pm_kernel<9>;
+                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+            } else if (dK == 10) {
+                auto kfn = nttp::lde_mid_pm_kernel<10>;
+                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+            } else {
+                auto kfn = nttp::lde_mid_pm_kernel<11>;
+                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+            }
+        } else if (dK == 9) {
             auto kfn = nttf::lde_mid_fast_kernel<9>;
             TS_LAUNCH(kfn, (unsigned)blocks, nttf::MID_NT, smem, c->stream, fp);
         } else if (dK == 10) {
@@ -465,7 +541,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
             auto kfn = nttf::lde_mid_fast_kernel<11>;
             TS_LAUNCH(kfn, (unsigned)blocks, nttf::MID_NT, smem, c->stream, fp);
         }
-        TS_TRY(check_launch(c, "lde_mid_fast_kernel"));
+        rc = check_launch(c, "lde_mid (fast) kernel");
     } else {
         ntt::MidParams p;
         p.src = D > 1 ? c->scratch : src;
@@ -491,17 +567,23 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         KScope ks(c, TS_K_LDE_MID);
         auto kfn = ntt::lde_mid_kernel;
         TS_LAUNCH(kfn, (unsigned)blocks, 512, smem, c->stream, p);
-        TS_TRY(check_launch(c, "lde_mid_kernel"));
+        rc = check_launch(c, "lde_mid_kernel");
     }
-    // forward passes over the remaining digits, all cosets at once
+    // forward passes over the remaining digits, all cosets at once; the last one writes the caller's matrix
     used = 0;
-    for (size_t i = 0; i + 1 < D; i++) {
+    for (size_t i = 0; i + 1 < D && rc == TS_OK; i++) {
         const int lo_bits = klo - used - dg[i];
         const int hi_bits = m + (int)b - lo_bits - dg[i];
-        TS_TRY(launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), dst_pitch, dst_pitch));
+        const bool last = i + 2 == D;
+        if (blocked)
+            rc = launch_pass(c, false, inter, last ? dst : inter, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), w,
+                             last ? dst_pitch : w, i_slice, last ? 0 : i_slice);
+        else
+            rc = launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), dst_pitch, dst_pitch);
         used += dg[i];
     }
-    return TS_OK;
+    if (inter) pool_release(c, inter);  // stream-ordered: later allocations on this stream may reuse it
+    return rc;
 }
 
 // Host trace -> committed LDE on the device, H2D overlapped with compute: the matrix is cut into column chunks;
@@ -842,9 +924,27 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttf::ntt_pass_fast_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 168 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
     // small twiddle table w_4096^e and the fold's 256-entry low table, built once
     bool ok = cudaMalloc((void **)&c->tw_small, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
               cudaMalloc((void **)&c->tw_small_inv, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
