@@ -98,7 +98,7 @@ def run_reference(a):
         "impl": "reference",
         "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u32 (BabyBear, exact modular arithmetic)", "data": "synthetic",
+        "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sample": cb["sample"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -303,12 +303,14 @@ def run_b200(a):
             roof = {"kernel": dom, "bound": "hbm", "achieved": per_launch_bytes / per_launch_s / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": per_launch_bytes / per_launch_s / 1e9 / peak, "traffic": traffic,
                     "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_s * 1e3, "peak_source": peak_src,
-                    "note": "rank 0 shard; NTT and Blake3 are INT32-issue bound (DESIGN.md), the HBM fraction is what the contract asks for"}
+                    "note": "rank 0's kernels; algorithmic bytes = compulsory I/O of that kernel class (DESIGN.md 4). The tile pattern's "
+                            "measured memory ceiling is 2.0-4.0 TB/s (profiles/r01/tile_copy_b200.jsonl) and the butterflies are "
+                            "INT32-issue bound; Blake3 leaves run the ALU pipe at 91.5 % (profiles/r01/v3_ncu_full.md)"}
         lde_ms = sum(per_kind.get(k, {}).get("ms_per_step", 0) for k in ("ntt_pass", "lde_mid"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 (BabyBear Montgomery, exact modular arithmetic)", "data": "synthetic",
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "log_rows": a.log_rows, "width": a.width, "log_blowup": a.log_blowup,
                        "l2_policy": "inputs_larger_than_L2 (4 GiB trace, 16 GiB LDE; nothing is reused across steps)",
                        "parallelism": runner.parallelism, "fri_rounds": last["rounds"] if last else None},

@@ -682,7 +682,7 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
             fast = shifts[i] == 0 && mats[i]->width == mats[0]->width;
             total += mats[i]->width;
         }
-        if (fast && mats.size() > 1) fast = (mats[0]->width & (mats[0]->width - 1)) == 0 && mats[0]->width >= 16;
+        if (fast && mats.size() > 1) fast = (mats[0]->width & (mats[0]->width - 1)) == 0 && mats[0]->width >= 4;
         if (fast && total <= ((size_t)256 << b3::MAX_STACK)) {
             b3::FastSegs fs;
             for (int i = 0; i < b3::MAX_SEG; i++) fs.ptr[i] = i < (int)mats.size() ? mats[i]->d : nullptr;

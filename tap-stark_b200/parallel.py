@@ -83,9 +83,9 @@ class ShardedProver:
 
     def _chunks(self, wl: int) -> int:
         """column chunks per rank: the LDE of chunk c+1 overlaps the all-to-all of chunk c (NCCL runs on its own
-        stream).  Chunk widths stay powers of two >= 16 so the received blocks feed the fast leaf kernel."""
+        stream).  Chunk widths stay powers of two >= 8 so the received blocks feed the fast leaf kernel."""
         c = 1
-        while c < 4 and wl % (2 * c) == 0 and wl // (2 * c) >= 16 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
+        while c < 4 and wl % (2 * c) == 0 and wl // (2 * c) >= 8 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
             c *= 2
         return c if self.world > 1 else 1
 
