@@ -226,3 +226,90 @@ def test_full_pipeline_config1(ts, ctx, orc):
     w1, w2 = ch.grind(8), rch.grind(8)
     assert w1 == w2
     assert [ch.sample_bits(12) for _ in range(16)] == [rch.sample_bits(12) for _ in range(16)]
+
+
+# ---------------------------------------------------------------- BASELINE.json configs 3-5 (shapes named there)
+def test_config4_shape_reduced_height(ts, ctx, orc):
+    """Config 4 shape at an oracle-friendly height: ~200-column trace + degree-4 extension quotient as 4 chunks
+    of 4 base columns (uni-stark/src/prover.rs:78-83: chunk i has domain shift g * w^i), one commit each."""
+    log_n, b = 14, 2
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(b, 28, 8, mm))
+    trace = orc.splitmix_matrix(4, 1 << log_n, 200)
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(1 << log_n), ts.DeviceMatrix.from_canonical(ctx, trace))])
+    assert root == orc.mmcs_commit([orc.pcs_lde_committed(trace, b)]).root
+    # quotient chunks: domain shift 31 * w_{4n}^i, i = 0..3  ->  LDE shift 31 / (31 w^i) = w^-i
+    w4n = orc.two_adic_generator(log_n + 2)
+    chunks = [orc.splitmix_matrix(10 + i, 1 << log_n, 4) for i in range(4)]
+    doms = [ts.TwoAdicMultiplicativeCoset(log_n, 31 * pow(w4n, i, P) % P) for i in range(4)]
+    rootq, dataq = pcs.commit([(d, ts.DeviceMatrix.from_canonical(ctx, c)) for d, c in zip(doms, chunks)])
+    ldes = [orc.pcs_lde_committed(c, b, pow(pow(w4n, i, P), P - 2, P)) for i, c in enumerate(chunks)]
+    assert rootq == orc.mmcs_commit(ldes).root
+    rows, path = mm.open_batch(12345, dataq)
+    mm.verify_batch([1 << (log_n + b)] * 4, rows, 12345, path, rootq)
+
+
+def test_config4_full_height_properties(ts, ctx, orc):
+    """2^21 x 200, log_blowup 2 (RISC0-recursion scale): column-subset LDE parity, openings verify on the host."""
+    log_n, w, b = 21, 200, 2
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    t = torch.randint(0, P, (1 << log_n, w), dtype=torch.int32, device="cuda", generator=g)
+    torch.cuda.synchronize()
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(b, 28, 8, mm))
+    ev = ts.DeviceMatrix.wrap_device(ctx, t.data_ptr(), 1 << log_n, w, keepalive=t)
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(1 << log_n), ev)])
+    lde = mm.get_matrices(data)[0]
+    cols = [0, 7, 8, 199]
+    host_cols = ts.from_monty(t[:, cols].cpu().numpy().view(np.uint32))
+    want = orc.pcs_lde_committed(np.ascontiguousarray(host_cols), b)
+    for r0 in (0, (1 << 23) - 4096, 3 << 21):
+        got = lde.to_canonical(r0, 4096)
+        assert np.array_equal(got[:, cols], want[r0 : r0 + 4096])
+    for idx in (0, 1, (1 << 23) - 1, 4242424):
+        rows, path = mm.open_batch(idx, data)
+        assert np.array_equal(rows[0][cols], want[idx])
+        mm.verify_batch([1 << 23], rows, idx, path, root)
+
+
+@pytest.mark.parametrize("log_len,log_blowup", [(18, 1), (20, 3), (22, 4), (24, 2)])
+def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
+    """FRI commit-phase sweep over BabyBear^4 codewords (config 5): the codeword is the LDE of a random
+    low-degree extension polynomial (made on the device), folded down to the final polynomial.  Up to 2^20 the
+    whole transcript is compared with the oracle; above, the library's own constancy check (prover.rs:130-134)
+    and a host replay of fold_row along one query path (two_adic_pcs.rs:87-114) must agree."""
+    import torch
+
+    log_n = log_len - log_blowup
+    g = torch.Generator(device="cuda")
+    g.manual_seed(log_len)
+    coeff_evals = torch.randint(0, P, (1 << log_n, 4), dtype=torch.int32, device="cuda", generator=g)
+    torch.cuda.synchronize()
+    ev = ts.DeviceMatrix.wrap_device(ctx, coeff_evals.data_ptr(), 1 << log_n, 4, keepalive=coeff_evals)
+    cw = ts.GpuDft(ctx).coset_lde_batch(ev, log_blowup, 31, committed_order=True)
+    cfg = ts.FriConfig(log_blowup, 4, 8, ts.Blake3MerkleMmcs(ctx))
+    ch = ts.BfChallenger()
+    res = ts.bf_commit_phase(cfg, [cw], ch)
+    assert len(res.commits) == log_n
+    if log_len <= 20:
+        ref = orc.fri_commit_phase([cw.to_canonical()], log_blowup, orc.BfChallenger())
+        assert ref["ok"] and res.commits == ref["commits"] and np.array_equal(res.final_poly, ref["final_poly"])
+        return
+    # replay: betas from the commitments, then fold_row along the path of one index using opened layer rows
+    rch = orc.BfChallenger()
+    idx, folded = 987654321 % (1 << log_len), None
+    for r, (commit, pd) in enumerate(zip(res.commits, res.data)):
+        rch.observe_digest(commit)
+        beta = rch.sample_ef()
+        pair = idx >> 1
+        rows, path = cfg.mmcs.open_batch(pair, pd)
+        cfg.mmcs.verify_batch([1 << (log_len - 1 - r)], rows, pair, path, commit)
+        e0, e1 = rows[0][:4], rows[0][4:]
+        if folded is not None:
+            assert np.array_equal(folded, e1 if idx & 1 else e0)
+        folded = orc.fold_row_ef(pair, log_len - 1 - r, beta, e0, e1)
+        idx = pair
+    assert np.array_equal(folded, res.final_poly)
