@@ -192,6 +192,20 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *ctx, const ts_tree *t, size_t idx, 
 int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out);
 
 
+/* ---------------------------------------------------------------- reduced openings: TwoAdicFriPcs::open (f1)
+ * The pass between the commitments and FRI (fri/src/two_adic_pcs.rs:312-389), on the device-resident LDE. */
+/* compute_inverse_denominators (:677-720): out[X] = 1 / (x_X - z), x_X = g * w_h^bitrev(X), h = 2^log_h, as an
+ * h x 4 matrix.  Smaller heights use its first rows (bit-reversed cosets nest). */
+int ts_inv_denoms(ts_ctx *ctx, unsigned log_h, const uint32_t z_monty[4], ts_matrix **out);
+/* interpolate_coset (:358-369): ys[c] = p_c(z) from the low coset = the first n committed rows of `lde`;
+ * inv_denoms from ts_inv_denoms for the same z.  ys_out_monty: width x 4 u32 (host). */
+int ts_interpolate_low_coset(ts_ctx *ctx, const ts_matrix *lde, size_t n, const uint32_t z_monty[4],
+                             const ts_matrix *inv_denoms, uint32_t *ys_out_monty);
+/* "reduce rows" (:371-381): ro[X] += alpha_pow_offset * (dot[X] - reduced_ys) * inv_denoms[X] */
+int ts_reduce_opening_acc(ts_ctx *ctx, const ts_matrix *dot, const ts_matrix *inv_denoms,
+                          const uint32_t alpha_pow_offset_monty[4], const uint32_t reduced_ys_monty[4], ts_matrix *ro);
+int ts_matrix_zero(ts_ctx *ctx, ts_matrix *m);
+
 /* ---------------------------------------------------------------- sharded building blocks (one process per GPU)
  * The path shards as SURVEY 8(e): LDE by columns (no communication), one all-to-all to re-shard by rows,
  * hashing / alpha-reduction / folding on contiguous row ranges; sub-roots are all-gathered (32 bytes per rank)

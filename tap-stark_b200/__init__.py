@@ -106,6 +106,10 @@ _SIGNATURES = {
     "ts_pcs_commit_host": (C.c_int, [_vp, _vpp, _szp, _szp, _vp, C.c_size_t, C.c_uint, C.c_int, _u8p, _vpp]),
     "ts_pcs_get_evaluations_on_domain": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp]),
     "ts_dot_ext_powers": (C.c_int, [_vp, _vp, _vp, _vpp]),
+    "ts_inv_denoms": (C.c_int, [_vp, C.c_uint, _vp, _vpp]),
+    "ts_interpolate_low_coset": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "ts_reduce_opening_acc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "ts_matrix_zero": (C.c_int, [_vp, _vp]),
     "ts_coset_lde_batch_into": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint32, _vp]),
     "ts_alpha_powers": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
@@ -626,3 +630,134 @@ class TwoAdicFriPcs:
         h = C.c_void_p()
         self.ctx.check(self.ctx._L.ts_dot_ext_powers(self.ctx._h, m._h, _ptr(a), C.byref(h)), "dot_ext_powers")
         return DeviceMatrix(self.ctx, h)
+
+
+# ------------------------------------------------------------------------------------------- open / prove (f1, f4)
+def _ef_mul(a, b):
+    """BabyBear^4 product on canonical Python ints (transcript-side arithmetic: a few hundred per proof)."""
+    r = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            r[i + j] = (r[i + j] + int(a[i]) * int(b[j])) % P
+    return [(r[i] + 11 * r[i + 4]) % P if i < 3 else r[i] for i in range(4)]
+
+
+def _ef_pow(a, e: int):
+    r, b = [1, 0, 0, 0], [int(x) for x in a]
+    while e:
+        if e & 1:
+            r = _ef_mul(r, b)
+        b = _ef_mul(b, b)
+        e >>= 1
+    return r
+
+
+@dataclass
+class BatchOpening:
+    """[MEM] p3_fri::BatchOpening as used at fri/src/two_adic_pcs.rs:408-411"""
+
+    opened_values: List[np.ndarray]
+    opening_proof: np.ndarray
+
+
+@dataclass
+class BfQueryProof:
+    """fri/src/proof.rs:23-33"""
+
+    input_proof: List[BatchOpening]
+    commit_phase_openings: List[Tuple[List[np.ndarray], np.ndarray]]
+
+
+@dataclass
+class FriProof:
+    """fri/src/proof.rs:13-21"""
+
+    commit_phase_commits: List[bytes]
+    query_proofs: List[BfQueryProof]
+    final_poly: np.ndarray
+    pow_witness: int
+
+
+def bf_prove(config: FriConfig, inputs: Sequence[DeviceMatrix], challenger: BfChallenger, open_input) -> FriProof:
+    """fri/src/prover.rs:19-67: commit phase, proof-of-work grinding, query phase.
+    open_input(query_index) -> input proof.  (The reference's query_times_index selects one of its num_queries
+    Taptrees; a Merkle commitment has a single tree.)"""
+    log_max_height = int(inputs[0].rows).bit_length() - 1
+    cp = bf_commit_phase(config, inputs, challenger)
+    pow_witness = challenger.grind(config.proof_of_work_bits)
+    queries = []
+    for _ in range(config.num_queries):
+        index = challenger.sample_bits(log_max_height)
+        openings = [config.mmcs.open_batch(index >> i >> 1, data) for i, data in enumerate(cp.data)]  # prover.rs:69-90
+        queries.append(BfQueryProof(open_input(index), openings))
+    return FriProof(cp.commits, queries, cp.final_poly, pow_witness)
+
+
+def _pcs_open(self, rounds, challenger: BfChallenger):
+    """TwoAdicFriPcs::open (fri/src/two_adic_pcs.rs:260-419) on the device-resident LDEs.
+    rounds: [(ProverData, [[point, ...] per matrix])], points = canonical BabyBear^4 (4 ints).
+    Returns (opened_values[round][matrix][point] -> (width, 4) canonical array, FriProof)."""
+    ctx, L, b = self.ctx, self.ctx._L, self.fri.log_blowup
+    alpha = [int(x) for x in challenger.sample()]  # :312
+    mats_and_points = [(self.mmcs.get_matrices(data), points) for data, points in rounds]
+    heights = [m.rows for mats, _ in mats_and_points for m in mats]
+    log_global_max_height = max(heights).bit_length() - 1
+    # inverse denominators per unique point, for the largest height opened at it (:677-720)
+    max_lh = {}
+    for mats, points in mats_and_points:
+        for m, pts in zip(mats, points):
+            for z in pts:
+                key = tuple(int(x) for x in z)
+                max_lh[key] = max(max_lh.get(key, 0), m.rows.bit_length() - 1)
+    inv = {}
+    for key, lh in max_lh.items():
+        zm = to_monty(np.array(key, dtype=np.uint32))
+        h = C.c_void_p()
+        ctx.check(L.ts_inv_denoms(ctx._h, lh, _ptr(zm), C.byref(h)), "inv_denoms")
+        inv[key] = DeviceMatrix(ctx, h)
+    reduced, num_reduced, opened = {}, {}, []
+    for mats, points in mats_and_points:
+        opened_round = []
+        for m, pts in zip(mats, points):
+            lh = m.rows.bit_length() - 1
+            if lh not in reduced:
+                ro = DeviceMatrix(ctx, _alloc(ctx, m.rows, 4))
+                ctx.check(L.ts_matrix_zero(ctx._h, ro._h), "matrix_zero")
+                reduced[lh], num_reduced[lh] = ro, 0
+            dot = self.dot_ext_powers(m, alpha) if pts else None  # sum_i alpha^i p_i[X], shared by all points (:375)
+            opened_mat = []
+            for z in pts:
+                key = tuple(int(x) for x in z)
+                zm = to_monty(np.array(key, dtype=np.uint32))
+                ys_m = np.empty((m.width, 4), dtype=np.uint32)
+                ctx.check(L.ts_interpolate_low_coset(ctx._h, m._h, m.rows >> b, _ptr(zm), inv[key]._h, _ptr(ys_m)),
+                          "interpolate_low_coset")  # :358-369
+                ys = from_monty(ys_m)
+                apo = _ef_pow(alpha, num_reduced[lh])
+                rys, ap = [0, 0, 0, 0], [1, 0, 0, 0]
+                for y in ys:  # dot_product(alpha.powers(), ys)
+                    t = _ef_mul(ap, y)
+                    rys = [(rys[k] + t[k]) % P for k in range(4)]
+                    ap = _ef_mul(ap, alpha)
+                apo_m, rys_m = to_monty(np.array(apo, dtype=np.uint32)), to_monty(np.array(rys, dtype=np.uint32))
+                ctx.check(L.ts_reduce_opening_acc(ctx._h, dot._h, inv[key]._h, _ptr(apo_m), _ptr(rys_m), reduced[lh]._h),
+                          "reduce_opening_acc")  # :371-381
+                num_reduced[lh] += m.width
+                opened_mat.append(ys)
+            opened_round.append(opened_mat)
+        opened.append(opened_round)
+    fri_input = [reduced[lh] for lh in sorted(reduced, reverse=True)]  # :389
+
+    def open_input(index):
+        out = []
+        for data, _ in rounds:
+            log_max = self.mmcs.get_max_height(data).bit_length() - 1
+            vals, proof = self.mmcs.open_batch(index >> (log_global_max_height - log_max), data)  # :399-413
+            out.append(BatchOpening(vals, proof))
+        return out
+
+    proof = bf_prove(self.fri, fri_input, challenger, open_input)
+    return opened, proof
+
+
+TwoAdicFriPcs.open = _pcs_open

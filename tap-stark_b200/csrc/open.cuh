@@ -1,0 +1,130 @@
+// open.cuh -- the reduced-opening pass of TwoAdicFriPcs::open (fri/src/two_adic_pcs.rs:260-419), SURVEY row f1:
+// the step between the commitments and FRI.  It re-reads the committed LDE, so doing it on the device removes the
+// only reason to download the LDE.
+//
+//   inv_denoms        :677-720   1/(x_X - z) for the coset g*K_h in bit-reversed order (x base field, z extension)
+//   interpolate_coset :358-369   ys = p(z) from the low coset ([MEM] p3-interpolation; here the barycentric form
+//                                p(z) = ((z/g)^n - 1)/n * sum_i e_i x_i / (z - x_i), exact in the field)
+//   reduce rows       :371-381   ro[X] += alpha^off * (sum_i alpha^i p_i[X] - sum_i alpha^i y_i) * inv_denom[X]
+#pragma once
+#include "field.cuh"
+
+namespace opn {
+
+struct RootPows {
+    uint32_t v[28];  // v[k] = w_h^(2^k), Montgomery
+};
+TS_D uint32_t pow_from_table(const RootPows &rp, uint32_t e) {
+    uint32_t acc = bb::MONTY_ONE;
+    for (int k = 0; e; k++, e >>= 1)
+        if (e & 1) acc = bb::mmul(acc, rp.v[k]);
+    return acc;
+}
+TS_D uint32_t brev_bits(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+TS_D uint32_t bb_inv(uint32_t a) {  // a^(p-2), Montgomery in/out; p - 2 = 0x77ffffff
+    uint32_t r = bb::MONTY_ONE, b = a;
+    uint32_t e = bb::P - 2;
+    while (e) {
+        if (e & 1) r = bb::mmul(r, b);
+        b = bb::mmul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+// inverse in F_p[x]/(x^4 - W) through the tower F_p[y]/(y^2 - W), y = x^2 (one base-field inversion)
+TS_D ef::E4 ef_inv(const ef::E4 &a) {
+    using bb::add;
+    using bb::mmul;
+    using bb::sub;
+    const uint32_t W = bb::MONTY_W;
+    const uint32_t a0 = a.c[0], a1 = a.c[1], a2 = a.c[2], a3 = a.c[3];
+    const uint32_t a1a3 = mmul(a1, a3), a0a2 = mmul(a0, a2);
+    // norm to F_p[y]: n0 + n1 y = A^2 - y B^2, A = a0 + a2 y, B = a1 + a3 y
+    const uint32_t n0 = sub(add(mmul(a0, a0), mmul(W, mmul(a2, a2))), mmul(W, add(a1a3, a1a3)));
+    const uint32_t n1 = sub(add(a0a2, a0a2), add(mmul(a1, a1), mmul(W, mmul(a3, a3))));
+    const uint32_t d = bb_inv(sub(mmul(n0, n0), mmul(W, mmul(n1, n1))));
+    const uint32_t m0 = mmul(n0, d), m1 = bb::neg(mmul(n1, d));
+    ef::E4 r;
+    r.c[0] = add(mmul(a0, m0), mmul(W, mmul(a2, m1)));
+    r.c[2] = add(mmul(a0, m1), mmul(a2, m0));
+    r.c[1] = bb::neg(add(mmul(a1, m0), mmul(W, mmul(a3, m1))));
+    r.c[3] = bb::neg(add(mmul(a1, m1), mmul(a3, m0)));
+    return r;
+}
+TS_D ef::E4 ef_mul_full(const ef::E4 &a, const ef::E4 &b) { return ef::mul(a, ef::prepare(b)); }
+
+// out[X] = 1 / (g * w_h^bitrev(X) - z)
+__global__ void __launch_bounds__(256) inv_denoms_kernel(uint4 *out, int log_h, uint32_t g_monty, RootPows rp, ef::E4 z) {
+    const size_t h = (size_t)1 << log_h;
+    for (size_t X = (size_t)blockIdx.x * blockDim.x + threadIdx.x; X < h; X += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)X, log_h)));
+        ef::E4 d;
+        d.c[0] = bb::sub(x, z.c[0]);
+        d.c[1] = bb::neg(z.c[1]);
+        d.c[2] = bb::neg(z.c[2]);
+        d.c[3] = bb::neg(z.c[3]);
+        const ef::E4 r = ef_inv(d);
+        out[X] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
+    }
+}
+
+// Barycentric column sums over the low coset: partial[blk][c] = sum_{r in block rows} e[r][c] * k_r,
+// k_r = x_r * inv_denom[r] (the sign and the (z/g)^n - 1)/n factor are applied by the caller).
+// One thread per column (coalesced row reads), RB rows per CTA, k_r staged in shared memory.
+constexpr int BARY_RB = 128;
+__global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__restrict__ m, size_t n, uint32_t width, int log_h,
+                                                          uint32_t g_monty, RootPows rp, const uint4 *__restrict__ inv_denoms,
+                                                          uint4 *__restrict__ partial) {
+    TS_DYN_SMEM(uint32_t, ks);  // BARY_RB x 4
+    const size_t r0 = (size_t)blockIdx.x * BARY_RB;
+    for (int i = threadIdx.x; i < BARY_RB; i += blockDim.x) {
+        uint4 k = make_uint4(0, 0, 0, 0);
+        if (r0 + i < n) {
+            const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)(r0 + i), log_h)));
+            const uint4 d = inv_denoms[r0 + i];
+            k = make_uint4(bb::mmul(x, d.x), bb::mmul(x, d.y), bb::mmul(x, d.z), bb::mmul(x, d.w));
+        }
+        ks[4 * i + 0] = k.x; ks[4 * i + 1] = k.y; ks[4 * i + 2] = k.z; ks[4 * i + 3] = k.w;
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < width; c += blockDim.x) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (int i = 0; i < BARY_RB; i += 2) {
+            const uint32_t v0 = r0 + i < n ? m[(r0 + i) * width + c] : 0u;
+            const uint32_t v1 = r0 + i + 1 < n ? m[(r0 + i + 1) * width + c] : 0u;
+            TS_UNROLL
+            for (int k = 0; k < 4; k++)
+                acc[k] = bb::add(acc[k], bb::redc((uint64_t)v0 * ks[4 * i + k] + (uint64_t)v1 * ks[4 * i + 4 + k]));
+        }
+        partial[(size_t)blockIdx.x * width + c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+// ys[c] = sum_blk partial[blk][c]
+__global__ void __launch_bounds__(256) bary_final_kernel(const uint4 *__restrict__ partial, size_t n_blocks, uint32_t width,
+                                                        uint4 *__restrict__ ys) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= width) return;
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (size_t b = 0; b < n_blocks; b++) {
+        const uint4 p = partial[b * width + c];
+        acc[0] = bb::add(acc[0], p.x); acc[1] = bb::add(acc[1], p.y);
+        acc[2] = bb::add(acc[2], p.z); acc[3] = bb::add(acc[3], p.w);
+    }
+    ys[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// ro[X] += apo * (dot[X] - rys) * inv_denoms[X]
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const uint4 *__restrict__ dot, const uint4 *__restrict__ inv_denoms,
+                                                         ef::E4 apo, ef::E4 rys, size_t h, uint4 *__restrict__ ro) {
+    const ef::E4Const ka = ef::prepare(apo);
+    for (size_t X = (size_t)blockIdx.x * blockDim.x + threadIdx.x; X < h; X += (size_t)gridDim.x * blockDim.x) {
+        const uint4 dv = dot[X], iv = inv_denoms[X], rv = ro[X];
+        const ef::E4 d{{dv.x, dv.y, dv.z, dv.w}}, id{{iv.x, iv.y, iv.z, iv.w}}, r{{rv.x, rv.y, rv.z, rv.w}};
+        const ef::E4 t = ef::mul(ef_mul_full(ef::sub(d, rys), id), ka);
+        const ef::E4 o = ef::add(r, t);
+        ro[X] = make_uint4(o.c[0], o.c[1], o.c[2], o.c[3]);
+    }
+}
+
+}  // namespace opn

@@ -18,6 +18,7 @@
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
 #include "ntt_pm.cuh"
+#include "open.cuh"
 
 // ------------------------------------------------------------------------------------------------ structs
 struct ts_matrix {
@@ -1544,6 +1545,118 @@ int ts_dot_ext_powers_acc(ts_ctx *c, const ts_matrix *m, const ts_matrix *alpha_
     if (alpha_powers->width != 4 || first_power + ((m->width + 15) & ~(size_t)15) > alpha_powers->rows)
         TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_acc: alpha_powers too short (use ts_alpha_powers(total_width))");
     return dot_ext_powers_launch(c, m, alpha_powers->d + 4 * first_power, acc, accumulate);
+}
+
+// ---------------------------------------------------------------- reduced openings (TwoAdicFriPcs::open, f1)
+static opn::RootPows root_pows(int log_h) {
+    opn::RootPows rp;
+    uint32_t r = bb::two_adic_generator(log_h);
+    for (int k = 0; k < 28; k++) {
+        rp.v[k] = h_to_monty(r);
+        r = bb::cmul(r, r);
+    }
+    return rp;
+}
+static ef::E4 to_e4(const uint32_t v[4]) {
+    ef::E4 e;
+    for (int i = 0; i < 4; i++) e.c[i] = v[i];
+    return e;
+}
+int ts_inv_denoms(ts_ctx *c, unsigned log_h, const uint32_t z_monty[4], ts_matrix **out) {
+    if (log_h > 27) TS_FAIL(c, TS_ERR_ARG, "inv_denoms: log_h > 27");
+    ts_matrix *o = nullptr;
+    TS_TRY(new_matrix(c, (size_t)1 << log_h, 4, &o));
+    {
+        KScope ks(c, TS_K_MISC);
+        const size_t h = (size_t)1 << log_h;
+        auto kfn = opn::inv_denoms_kernel;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>((h + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream, (uint4 *)o->d,
+                  (int)log_h, h_to_monty(31), root_pows((int)log_h), to_e4(z_monty));
+    }
+    int rc = check_launch(c, "inv_denoms_kernel");
+    if (rc != TS_OK) {
+        ts_matrix_free(o);
+        return rc;
+    }
+    *out = o;
+    return TS_OK;
+}
+int ts_interpolate_low_coset(ts_ctx *c, const ts_matrix *lde, size_t n, const uint32_t z_monty[4],
+                             const ts_matrix *inv_denoms, uint32_t *ys_out_monty) {
+    const int log_n = log2_strict(n), log_h = log2_strict(lde->rows);
+    if (log_n < 0 || log_h < 0 || n > lde->rows || inv_denoms->rows < n || inv_denoms->width != 4)
+        TS_FAIL(c, TS_ERR_ARG, "interpolate_low_coset: bad sizes");
+    const size_t w = lde->width, n_blocks = (n + opn::BARY_RB - 1) / opn::BARY_RB;
+    uint4 *partial = nullptr, *ys = nullptr;
+    TS_CUDA(c, pool_alloc(c, (void **)&partial, n_blocks * w * 16));
+    cudaError_t e = pool_alloc(c, (void **)&ys, w * 16);
+    if (e != cudaSuccess) {
+        pool_release(c, partial);
+        TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    int rc;
+    {
+        // the low coset of the committed LDE: rows r < n hold p(g * w_n^bitrev_n(r))
+        KScope ks(c, TS_K_MISC);
+        auto kfn = opn::bary_partial_kernel;
+        TS_LAUNCH(kfn, (unsigned)n_blocks, 256, (size_t)opn::BARY_RB * 16, c->stream, (const uint32_t *)lde->d, n, (uint32_t)w,
+                  log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial);
+        rc = check_launch(c, "bary_partial_kernel");
+    }
+    if (rc == TS_OK) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = opn::bary_final_kernel;
+        TS_LAUNCH(kfn, (unsigned)((w + 255) / 256), 256, 0, c->stream, (const uint4 *)partial, n_blocks, (uint32_t)w, ys);
+        rc = check_launch(c, "bary_final_kernel");
+    }
+    std::vector<uint32_t> s(w * 4);
+    if (rc == TS_OK) {
+        e = cudaMemcpyAsync(s.data(), ys, w * 16, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            c->err = cudaGetErrorString(e);
+            rc = TS_ERR_CUDA;
+        }
+    }
+    pool_release(c, partial);
+    pool_release(c, ys);
+    if (rc != TS_OK) return rc;
+    // ys = -((z/g)^n - 1)/n * S   (host: a handful of extension-field operations on `width` values)
+    uint32_t zc[4], t[4], f[4];
+    const uint32_t ginv = bb::cinv(31);
+    for (int i = 0; i < 4; i++) zc[i] = bb::cmul(h_from_monty(z_monty[i]), ginv);
+    memcpy(t, zc, 16);
+    for (int k = 0; k < log_n; k++) {
+        uint32_t sq[4];
+        h_ef_mul(t, t, sq);
+        memcpy(t, sq, 16);
+    }
+    t[0] = (t[0] + bb::P - 1) % bb::P;  // (z/g)^n - 1
+    const uint32_t fac = (bb::P - bb::cinv((uint32_t)(n % bb::P))) % bb::P;  // -1/n
+    for (int i = 0; i < 4; i++) f[i] = bb::cmul(t[i], fac);
+    for (size_t col = 0; col < w; col++) {
+        uint32_t sc[4], y[4];
+        for (int i = 0; i < 4; i++) sc[i] = h_from_monty(s[4 * col + i]);
+        h_ef_mul(sc, f, y);
+        for (int i = 0; i < 4; i++) ys_out_monty[4 * col + i] = h_to_monty(y[i]);
+    }
+    return TS_OK;
+}
+int ts_reduce_opening_acc(ts_ctx *c, const ts_matrix *dot, const ts_matrix *inv_denoms, const uint32_t alpha_pow_offset_monty[4],
+                          const uint32_t reduced_ys_monty[4], ts_matrix *ro) {
+    if (dot->width != 4 || ro->width != 4 || inv_denoms->width != 4 || dot->rows != ro->rows || inv_denoms->rows < ro->rows)
+        TS_FAIL(c, TS_ERR_ARG, "reduce_opening_acc: EF vectors of equal length expected");
+    KScope ks(c, TS_K_MISC);
+    const size_t h = ro->rows;
+    auto kfn = opn::reduce_rows_kernel;
+    TS_LAUNCH(kfn, (unsigned)std::min<size_t>((h + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream,
+              (const uint4 *)dot->d, (const uint4 *)inv_denoms->d, to_e4(alpha_pow_offset_monty), to_e4(reduced_ys_monty), h,
+              (uint4 *)ro->d);
+    return check_launch(c, "reduce_rows_kernel");
+}
+int ts_matrix_zero(ts_ctx *c, ts_matrix *m) {
+    TS_CUDA(c, cudaMemsetAsync(m->d, 0, m->rows * m->width * 4, c->stream));
+    return TS_OK;
 }
 
 // ---------------------------------------------------------------- sharded (multi-GPU) building blocks

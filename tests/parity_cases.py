@@ -187,3 +187,74 @@ def check_dot_ext_powers(ts, ctx, orc, rows, width, seed=8):
         acc = (acc + m[:, c : c + 1].astype(np.uint64) * cur.astype(np.uint64)) % P
         cur = orc.ef_mul(cur, alpha)
     assert np.array_equal(got, acc.astype(np.uint32))
+
+
+# ---- Pcs::open + verify (fri/src/two_adic_pcs.rs:260-530, fri/src/prover.rs, fri/src/verifier.rs) ------------------
+def check_pcs_open_verify(ts, ctx, orc, round_shapes, log_blowup, num_queries=6, pow_bits=4, seed=70):
+    """round_shapes: [[(log_n, width, n_points)] per commit round].  The device `open` must (1) return the
+    oracle's opened values, (2) feed FRI the oracle's reduced openings (same layer commitments / final poly) and
+    (3) produce a proof the restated reference verifier accepts; tampering must be rejected."""
+    from oracle import verifier as V
+
+    mmcs = ts.Blake3MerkleMmcs(ctx)
+    fri = ts.FriConfig(log_blowup, num_queries, pow_bits, mmcs)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, fri)
+    ch, och = ts.BfChallenger(), orc.BfChallenger()
+    rounds_dev, rounds_ora, commits = [], [], []
+    rng = np.random.default_rng(seed)
+    for ri, shapes in enumerate(round_shapes):
+        evs = [rand_mat(seed + 10 * ri + i, 1 << ln, w) for i, (ln, w, _) in enumerate(shapes)]
+        doms = [pcs.natural_domain_for_degree(1 << ln) for ln, _, _ in shapes]
+        root, data = pcs.commit([(d, ts.DeviceMatrix.from_canonical(ctx, e)) for d, e in zip(doms, evs)])
+        ldes = [orc.pcs_lde_committed(e, log_blowup) for e in evs]
+        assert root == orc.mmcs_commit(ldes).root
+        ch.observe(root)
+        och.observe_digest(root)
+        commits.append(root)
+        rounds_dev.append((data, shapes))
+        rounds_ora.append(ldes)
+    zeta = [int(x) for x in ch.sample()]
+    assert zeta == [int(x) for x in och.sample_ef()]
+    pts_dev, pts_ora = [], []
+    for (data, shapes), ldes in zip(rounds_dev, rounds_ora):
+        per_mat = []
+        for (ln, w, npts) in shapes:
+            wgen = orc.two_adic_generator(ln)
+            per_mat.append([[c * pow(wgen, k, P) % P for c in zeta] for k in range(npts)])  # zeta, zeta*w, ...
+        pts_dev.append((data, per_mat))
+        pts_ora.append(list(zip(ldes, per_mat)))
+    och_v = och.clone()
+    opened, proof = pcs.open(pts_dev, ch)
+    # (1)+(2): oracle's open
+    alpha = [int(x) for x in och.sample_ef()]
+    o_opened, o_reduced = V.pcs_open_reduced(pts_ora, log_blowup, alpha)
+    for r_dev, r_ora in zip(opened, o_opened):
+        for m_dev, m_ora in zip(r_dev, r_ora):
+            for y_dev, y_ora in zip(m_dev, m_ora):
+                assert y_dev.tolist() == y_ora
+    fri_in = [o_reduced[lh] for lh in sorted(o_reduced, reverse=True)]
+    ref = orc.fri_commit_phase(fri_in, log_blowup, och)
+    assert ref["ok"] and proof.commit_phase_commits == ref["commits"]
+    assert proof.final_poly.tolist() == ref["final_poly"].tolist()
+    assert proof.pow_witness == och.grind(pow_bits)
+    # (3): restated reference verifier
+    v_rounds = []
+    for commit, (data, per_mat), (_, shapes), o_r in zip(commits, pts_dev, rounds_dev, opened):
+        v_rounds.append((commit, [(ln, list(zip(pts, ys))) for (ln, _, _), pts, ys in zip(shapes, per_mat, o_r)]))
+    assert V.pcs_verify(log_blowup, num_queries, pow_bits, v_rounds, proof, och_v.clone())
+    bad = proof.query_proofs[0].commit_phase_openings[0][0][0]
+    bad[0] = (int(bad[0]) + 1) % P
+    try:
+        V.pcs_verify(log_blowup, num_queries, pow_bits, v_rounds, proof, och_v.clone())
+    except V.VerifyError:
+        pass
+    else:
+        raise AssertionError("tampered proof accepted")
+    bad[0] = (int(bad[0]) - 1) % P
+    opened[0][0][0][0][0] = (int(opened[0][0][0][0][0]) + 1) % P  # wrong claimed p(zeta)
+    try:
+        V.pcs_verify(log_blowup, num_queries, pow_bits, v_rounds, proof, och_v.clone())
+    except V.VerifyError:
+        pass
+    else:
+        raise AssertionError("wrong opened value accepted")

@@ -146,3 +146,10 @@ def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
     pc.check_dot_ext_powers(ts, ctx, orc, 300, 72)   # width % 4 == 0: fast kernel, partial last block
     pc.check_dot_ext_powers(ts, ctx, orc, 33, 256)
+
+
+def test_pcs_open_verify(ts, ctx, orc):
+    # uni-stark shape (uni-stark/src/prover.rs:94-104): trace opened at zeta and zeta*w, quotient chunks at zeta
+    pc.check_pcs_open_verify(ts, ctx, orc, [[(5, 3, 2)], [(5, 4, 1), (5, 4, 1)]], 2)
+    # fri/tests/pcs.rs "many_different": mixed heights in one commit
+    pc.check_pcs_open_verify(ts, ctx, orc, [[(4, 2, 1), (6, 3, 1), (3, 2, 1)]], 1, seed=90)

@@ -313,3 +313,10 @@ def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
         folded = orc.fold_row_ef(pair, log_len - 1 - r, beta, e0, e1)
         idx = pair
     assert np.array_equal(folded, res.final_poly)
+
+
+def test_pcs_open_verify(ts, ctx, orc):
+    """TwoAdicFriPcs::open end to end on the device, accepted by the restated reference verifier (parity rung L5)."""
+    pc.check_pcs_open_verify(ts, ctx, orc, [[(5, 3, 2)], [(5, 4, 1), (5, 4, 1)]], 2)
+    pc.check_pcs_open_verify(ts, ctx, orc, [[(4, 2, 1), (6, 3, 1), (3, 2, 1)]], 1, seed=90)
+    pc.check_pcs_open_verify(ts, ctx, orc, [[(8, 12, 2)], [(8, 4, 1)]], 2, num_queries=16, pow_bits=8, seed=110)
