@@ -27,14 +27,32 @@ TS_D uint32_t rotr(uint32_t x, int n) {
 #endif
 }
 
+// Blake3 is bound by the alu pipe (LOP3 + SHF: 8 per G, and ptxas also puts the 6 additions there as IADD3/IADD:
+// ncu showed alu 91.5 % / fma 16 % active).  The additions are therefore issued as IMAD x * 1 + y on the otherwise
+// idle fma pipe; the multiplier 1 comes from constant memory so that ptxas cannot fold it back into an IADD.
+#if !defined(TS_EMULATE) && !defined(TS_B3_NO_FMA_ADDS)
+__constant__ uint32_t c_one = 1;
+TS_D uint32_t fadd(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(c_one), "r"(b));
+    return r;
+#else
+    return a + b;
+#endif
+}
+#else
+TS_D uint32_t fadd(uint32_t a, uint32_t b) { return a + b; }
+#endif
+
 #define TS_B3_G(a, b, c, d, mx, my) \
-    a = a + b + (mx);               \
+    a = fadd(fadd(a, b), (mx));     \
     d = rotr(d ^ a, 16);            \
-    c = c + d;                      \
+    c = fadd(c, d);                 \
     b = rotr(b ^ c, 12);            \
-    a = a + b + (my);               \
+    a = fadd(fadd(a, b), (my));     \
     d = rotr(d ^ a, 8);             \
-    c = c + d;                      \
+    c = fadd(c, d);                 \
     b = rotr(b ^ c, 7);
 
 // message schedule: word index used at (round, slot), i.e. the permutation applied r times
