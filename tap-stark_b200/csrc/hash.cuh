@@ -242,8 +242,12 @@ struct FastSegs {
     int n;
 };
 constexpr int FAST_WARPS = 8;
+// [blk_begin, blk_end) is the window of 64-byte blocks absorbed by this launch: the host->device pipeline hashes a
+// row incrementally as its column chunks arrive, the chaining value parked in `digests` between launches (rows of
+// at most one Blake3 chunk, so there is no subtree stack to carry).  A full hash is the window [0, total_blocks).
 __global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSegs fs, uint32_t width, size_t n_leaves,
-                                                                        int monty, uint32_t *digests) {
+                                                                        int monty, uint32_t *digests, uint32_t blk_begin,
+                                                                        uint32_t blk_end) {
     TS_DYN_SMEM(uint32_t, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *ws = sm + warp * 512;
@@ -254,7 +258,16 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSeg
     uint4 pf[4];
     uint32_t cv[8], stack[MAX_STACK][8];
     int sp = 0;
-    iv(cv);
+    if (blk_begin == 0) {
+        iv(cv);
+    } else if (leaf0 + lane < n_leaves) {
+        const uint4 *st = reinterpret_cast<const uint4 *>(digests + (leaf0 + lane) * 8);
+        const uint4 a = st[0], b = st[1];
+        cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w;
+        cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+    } else {
+        iv(cv);
+    }
 #define TS_FETCH(blk_)                                                                                        \
     TS_UNROLL                                                                                                 \
     for (int k = 0; k < 4; k++) {                                                                             \
@@ -265,8 +278,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSeg
                     ? *reinterpret_cast<const uint4 *>(fs.ptr[sgi] + (leaf0 + row) * fs.seg_w + off)         \
                     : make_uint4(0, 0, 0, 0);                                                                 \
     }
-    TS_FETCH(0u)
-    for (uint32_t blk = 0; blk < total_blocks; blk++) {
+    TS_FETCH(blk_begin)
+    for (uint32_t blk = blk_begin; blk < blk_end; blk++) {
         TS_UNROLL
         for (int k = 0; k < 4; k++) {
             const uint32_t row = r0 + 8 * k;
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSeg
             *reinterpret_cast<uint4 *>(ws + row * 16 + 4 * (sub ^ ((row >> 1) & 3u))) = v;
         }
         __syncwarp();
-        if (blk + 1 < total_blocks) { TS_FETCH(blk + 1) }
+        if (blk + 1 < blk_end) { TS_FETCH(blk + 1) }
         uint32_t m[16];
         TS_UNROLL
         for (int j = 0; j < 4; j++) {

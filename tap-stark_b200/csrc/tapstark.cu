@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <functional>
 #include <vector>
 
 #include "fold.cuh"
@@ -594,15 +595,51 @@ size_t chunk_cols() {
     if (const char *e = getenv("TS_CHUNK_COLS")) return (size_t)strtoul(e, nullptr, 10);  // test hook
     return 64;
 }
+bool taper_last_chunk() { return getenv("TS_NO_TAPER") == nullptr; }
 bool pipeline_eligible(size_t n, size_t w) {
     const int m = log2_strict(n);
     const size_t wc = chunk_cols();
     return m >= 18 && wc >= 8 && w >= 2 * wc && (w & 3) == 0 && all_digits_fast(m, wc) &&
            (w % wc == 0 || all_digits_fast(m, w % wc)) && getenv("TS_NO_PIPELINE") == nullptr;
 }
+// Leaf hashing of ONE matrix restricted to the 64-byte blocks [blk_begin, blk_end) of every row; the chaining value
+// lives in `digests` between calls (hash.cuh: hash_rows_fast_kernel).  Rows of at most one Blake3 chunk.
+int hash_rows_window(ts_ctx *c, const uint32_t *mat, size_t width, size_t n_leaves, uint32_t *digests, uint32_t blk_begin,
+                     uint32_t blk_end) {
+    b3::FastSegs fs;
+    for (int i = 0; i < b3::MAX_SEG; i++) fs.ptr[i] = i == 0 ? mat : nullptr;
+    fs.n = 1;
+    fs.seg_w = (uint32_t)width;
+    fs.log_seg_w = 0;
+    KScope ks(c, TS_K_HASH_LEAVES);
+    auto kfn = b3::hash_rows_fast_kernel;
+    const size_t per_block = (size_t)b3::FAST_WARPS * 32;
+    TS_LAUNCH(kfn, (unsigned)((n_leaves + per_block - 1) / per_block), b3::FAST_WARPS * 32, (size_t)b3::FAST_WARPS * 512 * 4,
+              c->stream, fs, (uint32_t)width, n_leaves, 1, digests, blk_begin, blk_end);
+    return check_launch(c, "hash_rows_fast_kernel");
+}
+// rows the pipeline may hash chunk by chunk: one Blake3 chunk (<= 256 words), 16-byte aligned row segments
+bool incremental_hash_eligible(size_t w) {
+    return w <= 256 && (w & 3) == 0 && chunk_cols() % 16 == 0 && getenv("TS_NO_FAST") == nullptr &&
+           getenv("TS_NO_INC_HASH") == nullptr;
+}
+
+// leaf_digests != nullptr: also absorb every finished chunk into the row hashes (incremental_hash_eligible(w)), so
+// that only the last chunk's blocks remain to be hashed when the copy ends.
 int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w, unsigned b, uint32_t shift_monty,
-                            uint32_t *dst) {
-    const size_t wc = chunk_cols(), nchunks = (w + wc - 1) / wc;
+                            uint32_t *dst, uint32_t *leaf_digests = nullptr) {
+    const size_t wc = chunk_cols();
+    // chunk schedule: (first column, columns).  Everything after the last copy is exposed latency, so the final
+    // full chunk is cut in two (TS_NO_TAPER disables): narrower 2-D copies are slower on PCIe (profiles/r01/h2d_2d_b200.jsonl:
+    // 256-byte segments 55.6 GB/s, 128-byte 47.7, 64-byte 25), which bounds how far tapering pays.
+    std::vector<std::pair<size_t, size_t>> sched;
+    for (size_t c0 = 0; c0 < w; c0 += wc) sched.push_back({c0, std::min(wc, w - c0)});
+    if (taper_last_chunk() && sched.back().second == wc && wc % 32 == 0 && all_digits_fast(log2_strict(n), wc / 2)) {
+        const size_t c0 = sched.back().first;
+        sched.back() = {c0, wc / 2};
+        sched.push_back({c0 + wc / 2, wc / 2});
+    }
+    const size_t nchunks = sched.size();
     if (c->stage_words < n * wc) {
         TS_CUDA(c, cudaStreamSynchronize(c->stream));
         for (int s = 0; s < 2; s++) {
@@ -624,21 +661,24 @@ int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w,
 #endif
     for (size_t ch = 0; ch < nchunks; ch++) {
         const int s = (int)(ch & 1);
-        const size_t cols = std::min(wc, w - ch * wc);
+        const size_t col0 = sched[ch].first, cols = sched[ch].second;
 #ifndef TS_EMULATE
         if (c->ev_free_used[s]) TS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
 #endif
-        TS_CUDA(c, cudaMemcpy2DAsync(c->stage[s], cols * 4, host + ch * wc, w * 4, cols * 4, n, cudaMemcpyHostToDevice,
+        TS_CUDA(c, cudaMemcpy2DAsync(c->stage[s], cols * 4, host + col0, w * 4, cols * 4, n, cudaMemcpyHostToDevice,
                                      c->copy_stream));
 #ifndef TS_EMULATE
         TS_CUDA(c, cudaEventRecord(c->ev_copy[s], c->copy_stream));
         TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[s], 0));
 #endif
-        TS_TRY(lde_committed(c, c->stage[s], n, cols, b, shift_monty, dst + ch * wc, cols, w));
+        TS_TRY(lde_committed(c, c->stage[s], n, cols, b, shift_monty, dst + col0, cols, w));
 #ifndef TS_EMULATE
         TS_CUDA(c, cudaEventRecord(c->ev_free[s], c->stream));
         c->ev_free_used[s] = true;
 #endif
+        if (leaf_digests)
+            TS_TRY(hash_rows_window(c, dst, w, n << b, leaf_digests, (uint32_t)(col0 / 16),
+                                    (uint32_t)((col0 + cols + 15) / 16)));
     }
     return TS_OK;
 }
@@ -695,7 +735,8 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
             auto kfn = b3::hash_rows_fast_kernel;
             const size_t per_block = (size_t)b3::FAST_WARPS * 32;
             TS_LAUNCH(kfn, (unsigned)((n_leaves + per_block - 1) / per_block), b3::FAST_WARPS * 32,
-                      (size_t)b3::FAST_WARPS * 512 * 4, c->stream, fs, (uint32_t)total, n_leaves, 1, digests);
+                      (size_t)b3::FAST_WARPS * 512 * 4, c->stream, fs, (uint32_t)total, n_leaves, 1, digests, 0u,
+                      (uint32_t)((total + 15) / 16));
             return check_launch(c, "hash_rows_fast_kernel");
         }
     }
@@ -722,13 +763,14 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
     return check_launch(c, "hash_leaves_kernel");
 }
 
-int build_tree(ts_ctx *c, ts_tree *t) {
+// leaves_done: the leaf layer of t->digests was filled by the caller (pipelined commit: hash_rows_window)
+int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
     const size_t k = t->mats.size();
     size_t n_first = 0;
     if (t->layout == TS_LAYOUT_PADDED) n_first = k;
     else
         while (n_first < k && t->mats[t->order[n_first]]->rows == t->hmax) n_first++;
-    {
+    if (!leaves_done) {
         std::vector<const ts_matrix *> ms;
         std::vector<uint32_t> sh;
         for (size_t q = 0; q < n_first; q++) {
@@ -786,8 +828,11 @@ int build_tree(ts_ctx *c, ts_tree *t) {
     return TS_OK;
 }
 
+// fill_leaves (optional): called with the leaf-digest array once it is allocated; it produces the matrix AND its row
+// hashes (the host pipeline), after which only the levels above the leaves are built here.
 int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, int take_ownership,
-                uint8_t root[32], ts_tree **out, bool sync_root) {
+                uint8_t root[32], ts_tree **out, bool sync_root,
+                const std::function<int(uint32_t *)> *fill_leaves = nullptr) {
     if (n_mats == 0) TS_FAIL(ctx, TS_ERR_ARG, "mmcs: no matrices");
     ts_tree *t = new ts_tree;
     t->ctx = ctx;
@@ -818,7 +863,8 @@ int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, 
         ts_tree_free(t);
         TS_FAIL(ctx, TS_ERR_CUDA, std::string("cudaMalloc digests: ") + cudaGetErrorString(e));
     }
-    int rc = build_tree(ctx, t);
+    int rc = fill_leaves ? (*fill_leaves)(t->digests) : TS_OK;
+    if (rc == TS_OK) rc = build_tree(ctx, t, fill_leaves != nullptr);
     if (rc == TS_OK && root) {
         cudaError_t e2 = cudaMemcpyAsync(root, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToHost,
                                          ctx->stream);
@@ -1458,6 +1504,17 @@ int ts_pcs_commit_host(ts_ctx *c, const uint32_t *const *evals_host, const size_
         }
         const uint32_t shift = h_to_monty(bb::cmul(31, bb::cinv(dshift)));  // two_adic_pcs.rs:235
         ts_matrix *lde = nullptr;
+        if (n == 1 && pipeline_eligible(rows[i], widths[i]) && incremental_hash_eligible(widths[i])) {
+            // one matrix: rows are hashed chunk by chunk behind the copy, the tree is finished when the copy ends
+            rc = new_matrix(c, rows[i] << log_blowup, widths[i], &lde);
+            if (rc != TS_OK) break;
+            const std::function<int(uint32_t *)> fill = [&](uint32_t *leaf_digests) {
+                return lde_from_host_pipelined(c, evals_host[i], rows[i], widths[i], log_blowup, shift, lde->d, leaf_digests);
+            };
+            rc = mmcs_commit(c, &lde, 1, layout, 1, root, out, true, &fill);
+            if (rc != TS_OK) ts_matrix_free(lde);
+            return rc;
+        }
         if (pipeline_eligible(rows[i], widths[i])) {
             rc = new_matrix(c, rows[i] << log_blowup, widths[i], &lde);
             if (rc == TS_OK) rc = lde_from_host_pipelined(c, evals_host[i], rows[i], widths[i], log_blowup, shift, lde->d);

@@ -55,16 +55,21 @@ def test_lde_fast_path(ts, ctx, orc, log_n, width, b, digits, monkeypatch):
     pc.check_lde(ts, ctx, orc, log_n, width, b)
 
 
-def test_pcs_commit_host_pipelined(ts, ctx, orc, monkeypatch):
+@pytest.mark.parametrize("chunk,width", [(8, 20), (16, 40)])
+def test_pcs_commit_host_pipelined(ts, ctx, orc, monkeypatch, chunk, width):
     """ts_pcs_commit_host cuts a wide trace into column chunks (H2D of chunk k+1 overlaps the LDE of chunk k on the
-    GPU); each chunk is an LDE window into the full-width output.  TS_CHUNK_COLS shrinks the chunk for the emulator."""
+    GPU); each chunk is an LDE window into the full-width output.  TS_CHUNK_COLS shrinks the chunk for the emulator.
+    Chunks of 8, 8 and 4 columns: rows hashed after the LDE; chunks of 16, 16 and 8: rows hashed incrementally, one
+    64-byte Blake3 block per chunk, the chaining value parked in the leaf-digest array between launches."""
     import numpy as np
 
-    monkeypatch.setenv("TS_CHUNK_COLS", "8")
-    ev = pc.rand_mat(21, 1 << 18, 20)  # chunks of 8, 8 and 4 columns
+    monkeypatch.setenv("TS_CHUNK_COLS", str(chunk))
+    ev = pc.rand_mat(21, 1 << 18, width)
     mm = ts.Blake3MerkleMmcs(ctx)
     pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
+    ctx.reset_stats()
     root, data = pcs.commit_host([(pcs.natural_domain_for_degree(1 << 18), ts.to_monty(ev))])
+    assert ctx.stats()["hash_leaves"]["launches"] == (3 if chunk == 16 else 1)
     lde = orc.pcs_lde_committed(ev, 1)
     assert np.array_equal(mm.get_matrices(data)[0].to_canonical(), lde)
     assert root == orc.mmcs_commit([lde]).root

@@ -180,9 +180,10 @@ def test_pcs_commit(ts, ctx, orc):
     pc.check_pcs_commit(ts, ctx, orc, [(14, 40), (14, 4)], 2)
 
 
-@pytest.mark.parametrize("width", [192, 160])
+@pytest.mark.parametrize("width", [192, 160, 256, 320])
 def test_pcs_commit_host_pipelined(ts, ctx, orc, width):
-    """ts_pcs_commit_host on a trace wide enough for the H2D/LDE pipeline (64-column chunks, last one partial)."""
+    """ts_pcs_commit_host on a trace wide enough for the H2D/LDE pipeline (64-column chunks, last one partial).
+    Rows of at most one Blake3 chunk (<= 256 columns) are also hashed chunk by chunk behind the copy."""
     ev = orc.splitmix_matrix(9, 1 << 18, width)
     mm = ts.Blake3MerkleMmcs(ctx)
     pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
