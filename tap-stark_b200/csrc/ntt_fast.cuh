@@ -25,7 +25,20 @@ struct FastTables {
     const uint2 *tw_big;        // w_{2^big_log}^e
     int big_log;
     int small_log;
+    // product-indexed inter-round tables in global memory (ntt_pm.cuh rtw): rt[dir] holds, back to back,
+    // R1 tables for D = 9, 10, 11 ([row][g], 256 groups), the R2 table (8 x 32) and the R3 table (8 x 4);
+    // row r, group g = root^(g * brev(r)), root = w (dir 0) or w^-1 (dir 1) of the round's sub-transform size.
+    const uint2 *rt[2];
 };
+__host__ __device__ constexpr int RT_R1_OFF(int D) { return D == 9 ? 0 : D == 10 ? 2 * 256 : 6 * 256; }
+constexpr int RT_R2_OFF = 14 * 256, RT_R3_OFF = 15 * 256, RT_ENTRIES = 15 * 256 + 32;
+// dst[(row << logg) + g] = src[(g * brev(row)) << (small_log - logs)] for a round of 2^logs points in 2^logg groups
+__global__ void fill_round_table_kernel(uint2 *dst, const uint2 *src, int logs, int logg, int small_log) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (1u << logs)) return;
+    const uint32_t row = e >> logg, g = e & ((1u << logg) - 1);
+    dst[e] = src[(g * ntt::brev_bits(row, logs - logg)) << (small_log - logs)];
+}
 
 // Inter-round twiddle of register/digit `i` for butterfly group `g` in a round whose sub-transform has 2^LOGS
 // points and 2^LOGG groups: w_{2^LOGS}^(+-g*u).  SM = false: read-only global load from the 2^small_log table.

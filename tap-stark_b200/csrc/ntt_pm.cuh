@@ -94,28 +94,33 @@ TS_D void dft_v4(V4 (&x)[1 << LOGR]) {
     }
 }
 
-// inter-round twiddle of register i for group g: global power table, or a shared [i][g] table (lde_mid)
+// inter-round twiddle w^(+-g*u) of a round with 2^LOGS points in 2^LOGG groups.  SM: shared [i][g] table (8-column
+// lde_mid).  Otherwise the product-indexed global table (FastTables::rt): the lanes of a warp hold consecutive g, so
+// the load is one coalesced L1 hit instead of a 32-line gather out of a plain power table indexed by g*u.
 template <bool INV, bool SM, int LOGS, int LOGG>
 TS_D uint2 rtw(const FastTables &t, const uint2 *sm_tab, uint32_t g, uint32_t u, uint32_t i) {
     if (SM) return sm_tab[(i << LOGG) + g];
-    return __ldg((INV ? t.tw_small_inv : t.tw_small) + ((g * u) << (t.small_log - LOGS)));
+    constexpr int OFF = LOGS == 8 ? nttf::RT_R2_OFF : LOGS == 5 ? nttf::RT_R3_OFF : nttf::RT_R1_OFF(LOGS);
+    return __ldg(t.rt[INV ? 1 : 0] + OFF + ((uint32_t)brev_c((int)u, LOGS - LOGG) << LOGG) + g);
 }
 
-template <int D>
+// default tile: 2^D positions x 2^(14-D) columns = 64 KiB (NQv quads of 4 columns per position)
+__host__ __device__ constexpr int dnq(int D) { return (1 << (14 - D)) / 4; }
+template <int D, int NQv = dnq(D)>
 struct Geo {
     static constexpr int L = 1 << D;
-    static constexpr int K = 1 << (14 - D);       // lanes (columns) per tile
-    static constexpr int NQ = K / 4;              // quads per position
-    static constexpr int UNITS = NQ * L;          // 16-byte units per tile (64 KiB)
+    static constexpr int NQ = NQv;                // quads per position
+    static constexpr int K = 4 * NQ;              // lanes (columns) per tile
+    static constexpr int UNITS = NQ * L;          // 16-byte units per tile
     static constexpr int LOGR1 = D - 8;           // first-round radix (2, 4 or 8)
 };
 
 // ---- DIF rounds (forward direction of the data flow; INV only selects the roots) ---------------------------
 // R1: radix 2^(D-8), stride 256.  PRE (lde_mid): position c of the item is multiplied by pw[c] and by `lw`.
-template <int D, bool INV, bool PRE, bool SM, int NT>
+template <int D, bool INV, bool PRE, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dif_r1(const uint4 *src, uint4 *dst, const FastTables &t, const uint2 *sm_tab, const uint2 *pre_tab, uint2 lw,
                  int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
     for (int item = tid; item < 256 * G::NQ; item += NT) {
         const uint32_t g = item & 255, h = item >> 8;
@@ -135,9 +140,9 @@ TS_D void dif_r1(const uint4 *src, uint4 *dst, const FastTables &t, const uint2 
     }
 }
 // R2: radix 8 inside blocks of 256, stride 32: p = 256 blk + g + 32 c
-template <int D, bool INV, bool SM, int NT>
+template <int D, bool INV, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dif_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 8) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
@@ -154,9 +159,9 @@ TS_D void dif_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
     }
 }
 // R3: radix 8 inside blocks of 32, stride 4: p = 32 blk + g + 4 c
-template <int D, bool INV, bool SM, int NT>
+template <int D, bool INV, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dif_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 8) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
@@ -173,9 +178,9 @@ TS_D void dif_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
     }
 }
 // R4: radix 4 on consecutive positions p = 4 blk + c.  POST: inter-digit twiddle w^(+-lo*brev_D(p)) per position.
-template <int D, bool INV, bool POST, int NT>
+template <int D, bool INV, bool POST, int NT, int NQv = dnq(D)>
 TS_D void dif_r4(uint4 *tile, const FastTables &t, uint32_t lo, int tw_shift, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 4) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t blk = item & (G::L / 4 - 1), h = item / (G::L / 4);
@@ -200,9 +205,9 @@ TS_D void dif_r4(uint4 *tile, const FastTables &t, uint32_t lo, int tw_shift, in
 
 // ---- DIT rounds (inverse sub-transform of lde_mid: bit-reversed positions in, natural out) ------------------
 // block i of a round holds the sub-sequence with digit brev(i); digit c is multiplied by w^-(c j) before the DFT.
-template <int D, int NT>
+template <int D, int NT, int NQv = dnq(D)>
 TS_D void dit_r4(uint4 *tile, int tid) {  // radix 4, consecutive positions, no twiddles
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 4) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t blk = item & (G::L / 4 - 1), h = item / (G::L / 4);
@@ -215,9 +220,9 @@ TS_D void dit_r4(uint4 *tile, int tid) {  // radix 4, consecutive positions, no 
         for (int u = 0; u < 4; u++) st4(tile + (base ^ (uint32_t)u), v[brev_c(u, 2)]);
     }
 }
-template <int D, bool SM, int NT>
+template <int D, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dit_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 8, stride 4
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 8) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
@@ -236,9 +241,9 @@ TS_D void dit_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
         for (int u = 0; u < 8; u++) st4(tile + (base ^ (uint32_t)((4 * u) ^ ((u >> 1) & 3))), v[brev_c(u, 3)]);
     }
 }
-template <int D, bool SM, int NT>
+template <int D, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dit_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 8, stride 32
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 8) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t grp = item & (G::L / 8 - 1), h = item / (G::L / 8);
@@ -257,9 +262,9 @@ TS_D void dit_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
         for (int u = 0; u < 8; u++) st4(tile + ((u & 1) ? b1 : b0) + 32 * u, v[brev_c(u, 3)]);
     }
 }
-template <int D, bool SM, int NT>
+template <int D, bool SM, int NT, int NQv = dnq(D)>
 TS_D void dit_r1(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid) {  // radix 2^(D-8), stride 256
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
     for (int item = tid; item < 256 * G::NQ; item += NT) {
         const uint32_t j = item & 255, h = item >> 8;
@@ -286,10 +291,10 @@ TS_D size_t word_off(size_t row, uint32_t col, uint32_t pitch, size_t slice) {
 }
 
 // BREV: tile position q receives source row brev_D(q)
-template <int D, bool BREV, int NT>
+template <int D, bool BREV, int NT, int NQv = dnq(D)>
 TS_D void load_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
                     uint32_t ncols, uint32_t col0, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int TOTAL = G::L * G::NQ, U = TOTAL / NT;
     static_assert(TOTAL % NT == 0, "tile");
     uint4 val[U];
@@ -309,10 +314,10 @@ TS_D void load_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t ro
         tile[hx<D>(h) ^ sigma(q)] = val[u];
     }
 }
-template <int D, int NT>
+template <int D, int NT, int NQv = dnq(D)>
 TS_D void store_tile(const uint4 *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
                      uint32_t ncols, uint32_t col0, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int TOTAL = G::L * G::NQ;
     for (int it = tid; it < TOTAL; it += NT) {
         const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
@@ -323,11 +328,104 @@ TS_D void store_tile(const uint4 *tile, uint32_t *dst, size_t row_base, size_t r
     }
 }
 
+// ---- rounds fused with tile I/O ------------------------------------------------------------------------------
+// The first DIF round can take its operands straight from global memory and the last one can write its results
+// straight back: two of the five shared-memory round trips and two of the five barriers of a tile disappear.
+// Item order: NQ adjacent lanes cover one row (a full 32..128-byte segment per instruction); io_blk() permutes the
+// radix-4 blocks of a warp so that every quarter-warp still hits eight distinct 16-byte bank groups.
+template <int NQ>
+TS_D uint32_t io_blk(uint32_t j) {
+    if (NQ == 2) return (j & ~7u) | ((j & 3u) << 1) | ((j >> 2) & 1u);
+    if (NQ == 4) return (j & ~3u) | ((j & 1u) << 1) | ((j >> 1) & 1u);
+    return j;
+}
+template <int D, bool INV, int NT, int NQv = dnq(D)>
+TS_D void dif_r1_ld(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                    uint32_t ncols, uint32_t col0, const FastTables &t, int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
+    TS_UNROLL2
+    for (int item = tid; item < 256 * G::NQ; item += NT) {
+        const uint32_t h = item & (G::NQ - 1), g = item / G::NQ;
+        const uint32_t col = col0 + 4 * h;
+        V4 x[R];
+        TS_UNROLL
+        for (int c = 0; c < R; c++) {
+            const uint4 v = col < ncols
+                                ? nttf::ldg_tile(src + word_off(row_base + (size_t)(g + 256 * c) * row_stride, col, pitch, slice))
+                                : make_uint4(0, 0, 0, 0);
+            x[c] = V4{{v.x, v.y, v.z, v.w}};
+        }
+        dft_v4<LOGR, INV>(x);
+        TS_UNROLL
+        for (int i = 1; i < R; i++) x[i] = vmul(x[i], rtw<INV, false, D, 8>(t, nullptr, g, (uint32_t)brev_c(i, LOGR), i));
+        const uint32_t b0 = hx<D>(h) ^ sigma(g);
+        TS_UNROLL
+        for (int c = 0; c < R; c++) st4(tile + b0 + 256 * c, x[c]);
+    }
+}
+template <int D, bool INV, bool POST, int NT, int NQv = dnq(D)>
+TS_D void dif_r4_st(const uint4 *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                    uint32_t ncols, uint32_t col0, const FastTables &t, uint32_t lo, int tw_shift, int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int ITEMS = (G::L / 4) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t h = item & (G::NQ - 1), blk = io_blk<G::NQ>(item / G::NQ);
+        const uint32_t base = hx<D>(h) ^ (blk << 2) ^ ((blk >> 1) & 3u) ^ (((blk >> 3) & 1u) << 2);
+        uint2 pt[4];
+        if (POST) {
+            TS_UNROLL
+            for (int c = 0; c < 4; c++) pt[c] = btw<INV>(t, (lo * brev_bits(4 * blk + c, D)) << tw_shift);
+        }
+        V4 x[4];
+        TS_UNROLL
+        for (int c = 0; c < 4; c++) x[c] = ld4(tile + (base ^ (uint32_t)c));
+        dft_v4<2, INV>(x);
+        if (POST) {
+            TS_UNROLL
+            for (int c = 0; c < 4; c++) x[c] = vmul(x[c], pt[c]);
+        }
+        const uint32_t col = col0 + 4 * h;
+        if (col < ncols) {
+            TS_UNROLL
+            for (int c = 0; c < 4; c++)
+                st4(reinterpret_cast<uint4 *>(dst + word_off(row_base + (size_t)(4 * blk + c) * row_stride, col, pitch, slice)), x[c]);
+        }
+    }
+}
+
+// first DIT round of lde_mid straight from global memory: tile position q holds source row brev_D(q), so the four
+// operands of block blk are rows (c << (D-2)) | brev_(D-2)(blk), c = 0..3
+template <int D, int NT, int NQv = dnq(D)>
+TS_D void dit_r4_ld(uint4 *tile, const uint32_t *src, size_t row_base, uint32_t pitch, size_t slice, uint32_t ncols,
+                    uint32_t col0, int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int ITEMS = (G::L / 4) * G::NQ;
+    for (int item = tid; item < ITEMS; item += NT) {
+        const uint32_t h = item & (G::NQ - 1), blk = io_blk<G::NQ>(item / G::NQ);
+        const uint32_t base = hx<D>(h) ^ (blk << 2) ^ ((blk >> 1) & 3u) ^ (((blk >> 3) & 1u) << 2);
+        const uint32_t col = col0 + 4 * h, r0 = brev_bits(blk, D - 2);
+        V4 v[4];
+        TS_UNROLL
+        for (int c = 0; c < 4; c++) {
+            const uint4 t = col < ncols ? nttf::ldg_tile(src + word_off(row_base + r0 + ((size_t)c << (D - 2)), col, pitch, slice))
+                                        : make_uint4(0, 0, 0, 0);
+            v[c] = V4{{t.x, t.y, t.z, t.w}};
+        }
+        dft_v4<2, true>(v);
+        TS_UNROLL
+        for (int u = 0; u < 4; u++) st4(tile + (base ^ (uint32_t)u), v[brev_c(u, 2)]);
+    }
+}
+
 // ---- kernels ------------------------------------------------------------------------------------------------
 #ifndef TS_PM_PASS_MINBLOCKS
-#define TS_PM_PASS_MINBLOCKS 2
+#define TS_PM_PASS_MINBLOCKS 3
 #endif
-constexpr int PM_PASS_NT = 256;
+#ifndef TS_PM_PASS_NT
+#define TS_PM_PASS_NT 256
+#endif
+constexpr int PM_PASS_NT = TS_PM_PASS_NT;
 
 template <int D, bool INV>
 __global__ void __launch_bounds__(PM_PASS_NT, TS_PM_PASS_MINBLOCKS) ntt_pass_pm_kernel(nttf::FastPassParams p) {
@@ -336,7 +434,31 @@ __global__ void __launch_bounds__(PM_PASS_NT, TS_PM_PASS_MINBLOCKS) ntt_pass_pm_
     const uint32_t cs = blockIdx.x % p.n_col_slices, tile_id = blockIdx.x / p.n_col_slices;
     const uint32_t lo = tile_id & ((1u << p.lo_bits) - 1), hi = tile_id >> p.lo_bits;
     const uint32_t col0 = cs << (14 - D);
+#ifdef TS_EXP_SAMETILE  // timing experiment only: every CTA works on the same (L2-resident) tile
+    const size_t row_base = 0, row_stride = (size_t)1 << p.lo_bits;
+#else
     const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo, row_stride = (size_t)1 << p.lo_bits;
+#endif
+#ifdef TS_EXP_NOCOMPUTE  // timing experiment only: the tile I/O without the transform
+    load_tile<D, false, PM_PASS_NT>(tile, p.src, row_base, row_stride, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    __syncthreads();
+    store_tile<D, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
+    return;
+#endif
+#ifndef TS_PM_NO_FUSED_IO
+    dif_r1_ld<D, INV, PM_PASS_NT>(tile, p.src, row_base, row_stride, p.src_pitch, p.src_slice, p.ncols, col0, p.t, tid);
+    __syncthreads();
+    dif_r2<D, INV, false, PM_PASS_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    dif_r3<D, INV, false, PM_PASS_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    if (p.lo_bits > 0)
+        dif_r4_st<D, INV, true, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, p.t, lo,
+                                            p.tw_shift, tid);
+    else
+        dif_r4_st<D, INV, false, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, p.t, 0, 0,
+                                             tid);
+#else
     load_tile<D, false, PM_PASS_NT>(tile, p.src, row_base, row_stride, p.src_pitch, p.src_slice, p.ncols, col0, tid);
     __syncthreads();
     dif_r1<D, INV, false, false, PM_PASS_NT>(tile, tile, p.t, nullptr, nullptr, make_uint2(0, 0), tid);
@@ -349,6 +471,7 @@ __global__ void __launch_bounds__(PM_PASS_NT, TS_PM_PASS_MINBLOCKS) ntt_pass_pm_
     else dif_r4<D, INV, false, PM_PASS_NT>(tile, p.t, 0, 0, tid);
     __syncthreads();
     store_tile<D, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
+#endif
 }
 
 #ifndef TS_PM_MID_NT
@@ -370,7 +493,11 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
     uint2 *i2 = i1 + R1 * 256;
     uint2 *i3 = i2 + 256;
     const int tid = threadIdx.x;
+#ifdef TS_EXP_SAMETILE
+    const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = 0;
+#else
     const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = blockIdx.x / p.n_col_slices;
+#endif
     const uint32_t col0 = cs << (14 - D);
     const int m = D + p.klo_bits;
     const FastTables &t = p.t;
@@ -390,9 +517,21 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         i3[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 5)));
     }
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
+#if defined(TS_PM_NO_FUSED_IO) || defined(TS_EXP_NOCOMPUTE)
     load_tile<D, true, PM_MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, 1, p.src_pitch, p.src_slice, p.ncols, col0, tid);
     __syncthreads();
+#endif
+#ifdef TS_EXP_NOCOMPUTE
+    for (uint32_t j = 0; j < (1u << p.b); j++)
+        store_tile<D, PM_MID_NT>(A, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
+                                 p.dst_slice, p.ncols, col0, tid);
+    return;
+#endif
+#ifdef TS_PM_NO_FUSED_IO
     dit_r4<D, PM_MID_NT>(A, tid);
+#else
+    dit_r4_ld<D, PM_MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+#endif
     __syncthreads();
     dit_r3<D, true, PM_MID_NT>(A, t, i3, tid);
     __syncthreads();
@@ -408,13 +547,23 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         __syncthreads();
         dif_r3<D, false, true, PM_MID_NT>(W, t, f3, tid);
         __syncthreads();
+        const size_t row_base = ((size_t)brev_bits(j, p.b) << m) + Kc, row_stride = (size_t)1 << p.klo_bits;
+#ifdef TS_PM_NO_FUSED_IO
         if (p.klo_bits > 0) dif_r4<D, false, true, PM_MID_NT>(W, t, Kc, p.tw_shift, tid);
         else dif_r4<D, false, false, PM_MID_NT>(W, t, 0, 0, tid);
         __syncthreads();
-        store_tile<D, PM_MID_NT>(W, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
-                                 p.dst_slice, p.ncols, col0, tid);
+        store_tile<D, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
+#else
+        if (p.klo_bits > 0)
+            dif_r4_st<D, false, true, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, t, Kc,
+                                                 p.tw_shift, tid);
+        else
+            dif_r4_st<D, false, false, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, t, 0, 0,
+                                                  tid);
+#endif
     }
 }
+
 
 }  // namespace nttp
 
@@ -448,10 +597,10 @@ TS_D void cp_async_wait() {
 #endif
 }
 
-template <int D, bool BREV, int NT>
+template <int D, bool BREV, int NT, int NQv = dnq(D)>
 TS_D void prefetch_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
                         uint32_t ncols, uint32_t col0, int tid) {
-    using G = Geo<D>;
+    using G = Geo<D, NQv>;
     constexpr int TOTAL = G::L * G::NQ;
     TS_UNROLL
     for (int u = 0; u < TOTAL / NT; u++) {

@@ -37,6 +37,7 @@ struct ts_ctx {
     int num_sms = 148;
     uint2 *tw_small = nullptr;
     uint2 *tw_small_inv = nullptr;
+    uint2 *round_tab[2] = {nullptr, nullptr};  // nttf::FastTables::rt
     uint2 *tw_big = nullptr;
     int big_log = 0;
     uint32_t *fold_tlo = nullptr;
@@ -248,6 +249,8 @@ nttf::FastTables fast_tables(ts_ctx *c) {
     t.tw_big = c->tw_big;
     t.big_log = c->big_log;
     t.small_log = ntt::SMALL_LOG;
+    t.rt[0] = c->round_tab[0];
+    t.rt[1] = c->round_tab[1];
     return t;
 }
 bool fast_shape(int d, size_t w) {
@@ -998,6 +1001,18 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
               cudaMalloc((void **)&c->fold_tlo, 256 * 4) == cudaSuccess;
     if (ok) ok = gen_twiddles(c, c->tw_small, ntt::SMALL_LOG) == TS_OK;
     if (ok) ok = gen_twiddles(c, c->tw_small_inv, ntt::SMALL_LOG, true) == TS_OK;
+    for (int dir = 0; dir < 2 && ok; dir++) {  // product-indexed inter-round tables (ntt_pm.cuh: rtw)
+        ok = cudaMalloc((void **)&c->round_tab[dir], sizeof(uint2) * nttf::RT_ENTRIES) == cudaSuccess;
+        const uint2 *src = dir ? c->tw_small_inv : c->tw_small;
+        const int spec[5][3] = {{9, 8, nttf::RT_R1_OFF(9)}, {10, 8, nttf::RT_R1_OFF(10)}, {11, 8, nttf::RT_R1_OFF(11)},
+                                {8, 5, nttf::RT_R2_OFF}, {5, 2, nttf::RT_R3_OFF}};
+        for (int k = 0; k < 5 && ok; k++) {
+            auto kfn = nttf::fill_round_table_kernel;
+            TS_LAUNCH(kfn, ((1u << spec[k][0]) + 255) / 256, 256, 0, c->stream, c->round_tab[dir] + spec[k][2], src, spec[k][0],
+                      spec[k][1], (int)ntt::SMALL_LOG);
+            ok = check_launch(c, "fill_round_table_kernel") == TS_OK;
+        }
+    }
     if (ok) {
         uint32_t tlo[256];
         const uint32_t w512inv = bb::cinv(bb::two_adic_generator(9));
@@ -1022,6 +1037,8 @@ void ts_ctx_destroy(ts_ctx *c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->tw_small);
     cudaFree(c->tw_small_inv);
+    cudaFree(c->round_tab[0]);
+    cudaFree(c->round_tab[1]);
     cudaFree(c->tw_big);
     cudaFree(c->fold_tlo);
     cudaFree(c->scratch);
