@@ -147,10 +147,16 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__r
     }
 }
 
+// t < 2 p 2^32  ->  t mod (p 2^32) congruent, < p 2^32
+TS_D uint64_t fold64(uint64_t t) {
+    const uint32_t hi = (uint32_t)(t >> 32);
+    return ((uint64_t)bb::umin32(hi, hi - bb::P) << 32) | (uint32_t)t;
+}
+
 // Hot path of dot_ext_powers for matrices with width % 4 == 0 (the committed LDE): a warp owns 32 rows; per block
 // of 16 columns the lanes issue 4 coalesced LDG.128 each (one block ahead), transpose through a warp-private
-// XOR-swizzled 2 KiB buffer, and every lane accumulates its own row: products are summed in 64 bits in PAIRS
-// (2 p^2 < p 2^32 keeps the Montgomery reduction in range), so one reduction serves two columns.
+// XOR-swizzled 2 KiB buffer, and every lane accumulates its own row in four 64-bit sums (IMAD.WIDE), folded
+// below p 2^32 by a min on the high word every two products and Montgomery-reduced once per row.
 // apow must be padded with zeros to a multiple of 16 entries.
 constexpr int DOT_FAST_WARPS = 8;
 #ifndef TS_DOT_MINBLOCKS
@@ -167,7 +173,9 @@ __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_row
     const uint32_t total_blocks = (width + 15u) / 16u;
     const uint32_t sub = lane & 3, r0 = lane >> 2;
     uint4 pf[4];
-    uint32_t acc[4] = {0, 0, 0, 0};
+    // 64-bit running sums, kept below p * 2^32 (the Montgomery reduction's input range) by one conditional subtraction
+    // of p * 2^32 -- a min on the high word -- after every two products (2 p^2 + p 2^32 < 2 p 2^32 < 2^64)
+    uint64_t acc[4] = {0, 0, 0, 0};
 #define TS_DOT_FETCH(blk_)                                                                           \
     TS_UNROLL                                                                                        \
     for (int k = 0; k < 4; k++) {                                                                    \
@@ -195,20 +203,21 @@ __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_row
         TS_UNROLL
         for (int i = 0; i < 16; i += 2) {
             const uint4 a0 = __ldg(apow + 16 * blk + i), a1 = __ldg(apow + 16 * blk + i + 1);
-            acc[0] = bb::add(acc[0], bb::redc((uint64_t)v[i] * a0.x + (uint64_t)v[i + 1] * a1.x));
-            acc[1] = bb::add(acc[1], bb::redc((uint64_t)v[i] * a0.y + (uint64_t)v[i + 1] * a1.y));
-            acc[2] = bb::add(acc[2], bb::redc((uint64_t)v[i] * a0.z + (uint64_t)v[i + 1] * a1.z));
-            acc[3] = bb::add(acc[3], bb::redc((uint64_t)v[i] * a0.w + (uint64_t)v[i + 1] * a1.w));
+            acc[0] = fold64(acc[0] + (uint64_t)v[i] * a0.x + (uint64_t)v[i + 1] * a1.x);
+            acc[1] = fold64(acc[1] + (uint64_t)v[i] * a0.y + (uint64_t)v[i + 1] * a1.y);
+            acc[2] = fold64(acc[2] + (uint64_t)v[i] * a0.z + (uint64_t)v[i + 1] * a1.z);
+            acc[3] = fold64(acc[3] + (uint64_t)v[i] * a0.w + (uint64_t)v[i + 1] * a1.w);
         }
     }
 #undef TS_DOT_FETCH
     if (row0 + lane < rows) {
+        uint32_t r[4] = {bb::redc(acc[0]), bb::redc(acc[1]), bb::redc(acc[2]), bb::redc(acc[3])};
         if (accumulate) {
             const uint4 prev = out[row0 + lane];
-            acc[0] = bb::add(acc[0], prev.x); acc[1] = bb::add(acc[1], prev.y);
-            acc[2] = bb::add(acc[2], prev.z); acc[3] = bb::add(acc[3], prev.w);
+            r[0] = bb::add(r[0], prev.x); r[1] = bb::add(r[1], prev.y);
+            r[2] = bb::add(r[2], prev.z); r[3] = bb::add(r[3], prev.w);
         }
-        out[row0 + lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        out[row0 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
     }
 }
 

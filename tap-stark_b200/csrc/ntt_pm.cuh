@@ -364,16 +364,23 @@ TS_D void dif_r1_ld(uint4 *tile, const uint32_t *src, size_t row_base, size_t ro
         for (int c = 0; c < R; c++) st4(tile + b0 + 256 * c, x[c]);
     }
 }
-template <int D, bool INV, bool POST, int NT, int NQv = dnq(D)>
+// PSM: the post twiddles of this CTA's `lo` were staged in shared memory as two planes of uint4,
+// post[blk] = (w(4 blk), w(4 blk + 1)), post[L/4 + blk] = (w(4 blk + 2), w(4 blk + 3))  (lde_mid: same for all cosets)
+template <int D, bool INV, bool POST, int NT, int NQv = dnq(D), bool PSM = false>
 TS_D void dif_r4_st(const uint4 *tile, uint32_t *dst, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
-                    uint32_t ncols, uint32_t col0, const FastTables &t, uint32_t lo, int tw_shift, int tid) {
+                    uint32_t ncols, uint32_t col0, const FastTables &t, uint32_t lo, int tw_shift, int tid,
+                    const uint4 *post = nullptr) {
     using G = Geo<D, NQv>;
     constexpr int ITEMS = (G::L / 4) * G::NQ;
     for (int item = tid; item < ITEMS; item += NT) {
         const uint32_t h = item & (G::NQ - 1), blk = io_blk<G::NQ>(item / G::NQ);
         const uint32_t base = hx<D>(h) ^ (blk << 2) ^ ((blk >> 1) & 3u) ^ (((blk >> 3) & 1u) << 2);
         uint2 pt[4];
-        if (POST) {
+        if (POST && PSM) {
+            const uint4 a = post[blk], b = post[G::L / 4 + blk];
+            pt[0] = make_uint2(a.x, a.y); pt[1] = make_uint2(a.z, a.w);
+            pt[2] = make_uint2(b.x, b.y); pt[3] = make_uint2(b.z, b.w);
+        } else if (POST) {
             TS_UNROLL
             for (int c = 0; c < 4; c++) pt[c] = btw<INV>(t, (lo * brev_bits(4 * blk + c, D)) << tw_shift);
         }
@@ -492,6 +499,7 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
     uint2 *i1 = f3 + 32;                                  // inv (DIT) tables: w^-(c j)
     uint2 *i2 = i1 + R1 * 256;
     uint2 *i3 = i2 + 256;
+    uint4 *post = reinterpret_cast<uint4 *>(i3 + 32);    // post twiddles w_n^(Kc brev(p)), two planes (dif_r4_st)
     const int tid = threadIdx.x;
 #ifdef TS_EXP_SAMETILE
     const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = 0;
@@ -515,6 +523,16 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         const uint32_t i = e >> 2, g = e & 3;
         f3[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 5)));
         i3[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 5)));
+    }
+    // the inter-digit twiddles depend on (Kc, position) only: gathered once per CTA (2^D scattered 8-byte reads of the
+    // big table) instead of once per coset, and under the latency of the tile load that follows
+    if (p.klo_bits > 0) {
+        for (int e = tid; e < G::L / 2; e += PM_MID_NT) {
+            const uint32_t blk = e & (G::L / 4 - 1), c0 = 2 * (e / (G::L / 4));
+            const uint2 w0 = btw<false>(t, (Kc * brev_bits(4 * blk + c0, D)) << p.tw_shift);
+            const uint2 w1 = btw<false>(t, (Kc * brev_bits(4 * blk + c0 + 1, D)) << p.tw_shift);
+            post[e] = make_uint4(w0.x, w0.y, w1.x, w1.y);
+        }
     }
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
 #if defined(TS_PM_NO_FUSED_IO) || defined(TS_EXP_NOCOMPUTE)
@@ -555,8 +573,8 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         store_tile<D, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, tid);
 #else
         if (p.klo_bits > 0)
-            dif_r4_st<D, false, true, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, t, Kc,
-                                                 p.tw_shift, tid);
+            dif_r4_st<D, false, true, PM_MID_NT, dnq(D), true>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols,
+                                                               col0, t, Kc, p.tw_shift, tid, post);
         else
             dif_r4_st<D, false, false, PM_MID_NT>(W, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, t, 0, 0,
                                                   tid);

@@ -507,7 +507,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         fp.pre_tab = pre;
         fp.lane_tab = lane;
         const size_t blocks = ((size_t)1 << klo) * fp.n_col_slices;
-        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + 1024 + K) * sizeof(uint2);
+        const size_t smem = (size_t)2 * 16384 * 4 + (((size_t)2 << dK) + 1024 + K) * sizeof(uint2) + ((size_t)8 << dK);  // + post table
         KScope ks(c, TS_K_LDE_MID);
         if (use_pm() && use_persistent()) {
             nttp::PersistMidParams pp;
@@ -989,12 +989,12 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(nttp::lde_mid_pm2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
-    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    cudaFuncSetAttribute(nttp::lde_mid_pm_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
+    cudaFuncSetAttribute(nttf::lde_mid_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
     // small twiddle table w_4096^e and the fold's 256-entry low table, built once
     bool ok = cudaMalloc((void **)&c->tw_small, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
               cudaMalloc((void **)&c->tw_small_inv, sizeof(uint2) << ntt::SMALL_LOG) == cudaSuccess &&
