@@ -160,7 +160,7 @@ TS_D uint64_t fold64(uint64_t t) {
 // apow must be padded with zeros to a multiple of 16 entries.
 constexpr int DOT_FAST_WARPS = 8;
 #ifndef TS_DOT_MINBLOCKS
-#define TS_DOT_MINBLOCKS 3
+#define TS_DOT_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_rows_fast_kernel(const uint32_t *__restrict__ m, size_t rows,
                                                                           uint32_t width, const uint4 *__restrict__ apow,
