@@ -35,7 +35,7 @@ UNIT = "elems/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=22)
@@ -303,9 +303,10 @@ def run_b200(a):
             roof = {"kernel": dom, "bound": "hbm", "achieved": per_launch_bytes / per_launch_s / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": per_launch_bytes / per_launch_s / 1e9 / peak, "traffic": traffic,
                     "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_s * 1e3, "peak_source": peak_src,
-                    "note": "rank 0's kernels; algorithmic bytes = compulsory I/O of that kernel class (DESIGN.md 4). The tile pattern's "
-                            "measured memory ceiling is 2.0-4.0 TB/s (profiles/r01/tile_copy_b200.jsonl) and the butterflies are "
-                            "INT32-issue bound; Blake3 leaves run the ALU pipe at 91.5 % (profiles/r01/v3_ncu_full.md)"}
+                    "note": "rank 0's kernels; algorithmic bytes = compulsory I/O of that kernel class (DESIGN.md 4). The NTT kernels "
+                            "are INT32-issue/latency bound, not HBM bound: with every CTA on one L2-resident tile they take the same "
+                            "time (profiles/r01/README.md, 'compute-only' experiment); Blake3 leaves run the ALU pipe at 74 % and "
+                            "issue on 73 % of cycles (profiles/r01/v11_ncu_full.md)"}
         lde_ms = sum(per_kind.get(k, {}).get("ms_per_step", 0) for k in ("ntt_pass", "lde_mid"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
