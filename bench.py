@@ -240,6 +240,7 @@ def run_b200(a):
     barrier()
     ms = ev0.elapsed_time(ev1) / a.steps
     clocks = sampler.stop() if sampler else None
+    phases = runner.prover.last_phases() if hasattr(runner, "prover") else None
     stats = ctx.stats()
     launches = ctx.total_launches()
     ctx.set_profiling(False)
@@ -254,7 +255,7 @@ def run_b200(a):
     e2e = None
     if not a.no_e2e:
         runner.prepare_host()
-        for _ in range(2):
+        for _ in range(3):
             runner.step_e2e()
         barrier()
         k = max(2, min(a.steps, 5))
@@ -316,7 +317,7 @@ def run_b200(a):
                        "l2_policy": "inputs_larger_than_L2 (4 GiB trace, 16 GiB LDE; nothing is reused across steps)",
                        "parallelism": runner.parallelism, "fri_rounds": last["rounds"] if last else None},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "stages": per_kind,
+            "stages": per_kind, "phases_last_step_ms": phases,
             "lde_stage": {"alg_GB": alg["lde_stage_5B_per_elem"] / 1e9, "ms": lde_ms,
                           "achieved_GBs": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) if lde_ms else None,
                           "frac_of_hbm_peak": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) / peak if lde_ms else None},

@@ -220,6 +220,10 @@ int ts_alpha_powers(ts_ctx *ctx, const uint32_t alpha_monty[4], size_t count, ts
  * once per block with first_power = the block's first global column.  No host synchronisation. */
 int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const ts_matrix *alpha_powers, size_t first_power,
                           ts_matrix *acc, int accumulate);
+/* acc = sum over the concatenated columns of blocks[0..n_blocks) (equal row counts): one pass over all blocks
+ * when they have equal power-of-two widths (the column blocks of the all-to-all), else one pass per block. */
+int ts_dot_ext_powers_blocks(ts_ctx *ctx, ts_matrix *const *blocks, size_t n_blocks, const ts_matrix *alpha_powers,
+                             ts_matrix *acc);
 /* fold rows [first, first + h_local) of a layer of h_global rows (fold_matrix on a contiguous row range);
  * addend_dev (may be NULL) is the matching slice of the next FRI input. */
 int ts_fri_fold_ext_shard(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,

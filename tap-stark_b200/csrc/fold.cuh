@@ -162,8 +162,17 @@ constexpr int DOT_FAST_WARPS = 8;
 #ifndef TS_DOT_MINBLOCKS
 #define TS_DOT_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_rows_fast_kernel(const uint32_t *__restrict__ m, size_t rows,
-                                                                          uint32_t width, const uint4 *__restrict__ apow,
+// Several column blocks of EQUAL power-of-two width (what a rank holds after the all-to-all) are read as one row:
+// word cw of the row lives in block cw >> log_seg_w (same convention as b3::FastSegs).
+constexpr int DOT_MAX_SEG = 32;
+struct DotSegs {
+    const uint32_t *ptr[DOT_MAX_SEG];
+    uint32_t seg_w;
+    int log_seg_w;
+    int n;
+};
+__global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_rows_fast_kernel(DotSegs sg, size_t rows, uint32_t width,
+                                                                          const uint4 *__restrict__ apow,
                                                                           uint4 *__restrict__ out, int accumulate) {
     TS_DYN_SMEM(uint32_t, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,8 +189,10 @@ __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_row
     TS_UNROLL                                                                                        \
     for (int k = 0; k < 4; k++) {                                                                    \
         const uint32_t row = r0 + 8 * k, cw = 16u * (blk_) + 4u * sub;                               \
+        const uint32_t sgi = sg.n > 1 ? (cw >> sg.log_seg_w) : 0u;                                   \
+        const uint32_t off = sg.n > 1 ? (cw & (sg.seg_w - 1u)) : cw;                                 \
         pf[k] = (row0 + row < rows && cw < width)                                                    \
-                    ? *reinterpret_cast<const uint4 *>(m + (row0 + row) * width + cw)                \
+                    ? *reinterpret_cast<const uint4 *>(sg.ptr[sgi] + (row0 + row) * sg.seg_w + off)  \
                     : make_uint4(0, 0, 0, 0);                                                        \
     }
     TS_DOT_FETCH(0u)

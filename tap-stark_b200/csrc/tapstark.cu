@@ -1568,8 +1568,13 @@ static int dot_ext_powers_launch(ts_ctx *c, const ts_matrix *m, const uint32_t *
     if ((m->width & 3) == 0 && getenv("TS_NO_FAST") == nullptr) {
         auto kfn = fold::dot_rows_fast_kernel;
         const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
+        fold::DotSegs sg;
+        for (int i = 0; i < fold::DOT_MAX_SEG; i++) sg.ptr[i] = i == 0 ? m->d : nullptr;
+        sg.n = 1;
+        sg.seg_w = (uint32_t)m->width;
+        sg.log_seg_w = 0;
         TS_LAUNCH(kfn, (unsigned)((m->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
-                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, (const uint32_t *)m->d, m->rows, (uint32_t)m->width,
+                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, sg, m->rows, (uint32_t)m->width,
                   (const uint4 *)apow_dev, (uint4 *)o->d, accumulate);
         return check_launch(c, "dot_rows_fast_kernel");
     }
@@ -1619,6 +1624,42 @@ int ts_dot_ext_powers_acc(ts_ctx *c, const ts_matrix *m, const ts_matrix *alpha_
     if (alpha_powers->width != 4 || first_power + ((m->width + 15) & ~(size_t)15) > alpha_powers->rows)
         TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_acc: alpha_powers too short (use ts_alpha_powers(total_width))");
     return dot_ext_powers_launch(c, m, alpha_powers->d + 4 * first_power, acc, accumulate);
+}
+int ts_dot_ext_powers_blocks(ts_ctx *c, ts_matrix *const *blocks, size_t n_blocks, const ts_matrix *alpha_powers,
+                             ts_matrix *acc) {
+    if (n_blocks == 0) TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_blocks: no blocks");
+    size_t total = 0;
+    bool one_launch = n_blocks <= (size_t)fold::DOT_MAX_SEG && getenv("TS_NO_FAST") == nullptr;
+    for (size_t i = 0; i < n_blocks; i++) {
+        if (blocks[i]->rows != acc->rows) TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_blocks: row counts differ");
+        one_launch = one_launch && blocks[i]->width == blocks[0]->width;
+        total += blocks[i]->width;
+    }
+    const size_t w0 = blocks[0]->width;
+    one_launch = one_launch && w0 >= 4 && (w0 & (w0 - 1)) == 0;
+    if (acc->width != 4) TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_blocks: acc must be rows x 4");
+    if (alpha_powers->width != 4 || ((total + 15) & ~(size_t)15) > alpha_powers->rows)
+        TS_FAIL(c, TS_ERR_ARG, "dot_ext_powers_blocks: alpha_powers too short (use ts_alpha_powers(total_width))");
+    if (!one_launch) {  // ragged blocks: one accumulating pass per block
+        size_t first = 0;
+        for (size_t i = 0; i < n_blocks; i++) {
+            TS_TRY(ts_dot_ext_powers_acc(c, blocks[i], alpha_powers, first, acc, i > 0));
+            first += blocks[i]->width;
+        }
+        return TS_OK;
+    }
+    KScope ks(c, TS_K_MISC);
+    fold::DotSegs sg;
+    for (int i = 0; i < fold::DOT_MAX_SEG; i++) sg.ptr[i] = i < (int)n_blocks ? blocks[i]->d : nullptr;
+    sg.n = (int)n_blocks;
+    sg.seg_w = (uint32_t)w0;
+    sg.log_seg_w = log2_strict(w0);
+    auto kfn = fold::dot_rows_fast_kernel;
+    const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
+    TS_LAUNCH(kfn, (unsigned)((acc->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
+              (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, sg, acc->rows, (uint32_t)total, (const uint4 *)alpha_powers->d,
+              (uint4 *)acc->d, 0);
+    return check_launch(c, "dot_rows_fast_kernel");
 }
 
 // ---------------------------------------------------------------- reduced openings (TwoAdicFriPcs::open, f1)

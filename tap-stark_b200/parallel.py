@@ -120,6 +120,7 @@ class ShardedProver:
         gen = int(ts.to_monty(ts.GENERATOR))
         recv, works, keep = [], [], []
         staged = []
+        marks = [self._mark()]
         if host_panels is not None:
             # all panels are queued on a side stream up front; the main stream waits panel by panel
             if not hasattr(self, "_copy_stream"):
@@ -155,14 +156,15 @@ class ShardedProver:
         for w_ in works:
             w_.wait()
         del keep
+        marks.append(self._mark())  # LDE + re-shard done
         # global column order: rank-major, then chunk
-        blocks, first_col = [], []
+        blocks = []
         for s_ in range(G):
             for c in range(C_):
                 blocks.append(self._wrap(recv[c][s_], Nl, wc))
-                first_col.append(s_ * wl + c * wc)
         sub_root, data = self.mmcs.commit(blocks)
         root = self.combine_roots(sub_root)
+        marks.append(self._mark())  # leaf hashes, sub-tree, sub-root all-gather
         ch = ts.BfChallenger()
         ch.observe(root)
         alpha = ch.sample()
@@ -171,12 +173,33 @@ class ShardedProver:
         ctx.check(L.ts_alpha_powers(ctx._h, am.ctypes.data_as(C.c_void_p), wl * G, C.byref(ap)), "alpha_powers")
         fri_t = torch.empty((Nl, 4), dtype=torch.int32, device=self.device)
         fri = self._wrap(fri_t, Nl, 4)
-        for i, blk in enumerate(blocks):
-            ctx.check(L.ts_dot_ext_powers_acc(ctx._h, blk._h, ap, first_col[i], fri._h, int(i > 0)), "dot_ext_powers_acc")
+        # blocks are in global column order (first_col ascending and contiguous): one pass over all of them
+        arr = (C.c_void_p * len(blocks))(*[blk._h for blk in blocks])
+        ctx.check(L.ts_dot_ext_powers_blocks(ctx._h, arr, len(blocks), ap, fri._h), "dot_ext_powers_blocks")
         L.ts_matrix_free(ap)
         data.free()
+        marks.append(self._mark())  # alpha reduction
         commits, final = self._fri_commit_phase(fri_t, N, ch)
+        marks.append(self._mark())  # FRI commit phase
+        self._marks = marks
         return {"root": root, "commits": commits, "final_poly": final, "rounds": len(commits)}
+
+    PHASES = ("lde_and_reshard", "hash_tree_roots", "alpha_reduction", "fri_commit_phase")
+
+    def _mark(self):
+        if not self.torch.cuda.is_available():
+            return None
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def last_phases(self):
+        """Device time of the last step's phases in ms (CUDA events on the step's stream); None on CPU."""
+        m = getattr(self, "_marks", None)
+        if not m or m[0] is None:
+            return None
+        m[-1].synchronize()
+        return {k: m[i].elapsed_time(m[i + 1]) for i, k in enumerate(self.PHASES)}
 
     def _fri_commit_phase(self, cur_t, len_g: int, ch):
         """fri/src/prover.rs:93-141 on a row-sharded codeword (cur_t: this rank's [len_g/G, 4] slice)."""
