@@ -192,6 +192,22 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *ctx, const ts_tree *t, size_t idx, 
 int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out);
 
 
+/* ---------------------------------------------------------------- quotient values (f3)
+ * quotient_values of uni_stark::prove (uni-stark/src/prover.rs:122-194) on the device-resident trace LDE:
+ * for every point of the quotient domain g*H_m, m = 2^(log_n + log_quotient_degree) <= rows of the LDE, run the
+ * AIR's constraint program on (row i, row i + m/n) of get_evaluations_on_domain's view (two_adic_pcs.rs:247-258),
+ * fold the constraints with alpha (ProverConstraintFolder::assert_zero, uni-stark/src/folder.rs:60-64), divide by
+ * Z_H.  Output: 2^log_quotient_degree chunk matrices of (m >> log_quotient_degree) x 4 (flatten_to_base +
+ * split_evals, prover.rs:79-80), chunk k living on the coset g*w_m^k*H_n -- the input of the second ts_pcs_commit.
+ * Program: 4 words per instruction {op, dst, a, b}; operand = kind << 28 | index with kind 0 register (< 64),
+ * 1 local column, 2 next column, 3 public value, 4 constant, 5 selector (0 is_first_row, 1 is_last_row,
+ * 2 is_transition); op 0 ADD, 1 SUB, 2 MUL, 3 NEG, 4 ASSERT_ZERO(a).  Constants, public values and alpha are
+ * Montgomery form.  A malformed program is TS_ERR_ARG. */
+int ts_quotient_values(ts_ctx *ctx, const ts_matrix *trace_lde, unsigned log_n, unsigned log_quotient_degree,
+                       const uint32_t *program, size_t n_instr, const uint32_t *consts_monty, size_t n_consts,
+                       const uint32_t *public_values_monty, size_t n_public, const uint32_t alpha_monty[4],
+                       ts_matrix **chunks_out);
+
 /* ---------------------------------------------------------------- reduced openings: TwoAdicFriPcs::open (f1)
  * The pass between the commitments and FRI (fri/src/two_adic_pcs.rs:312-389), on the device-resident LDE. */
 /* compute_inverse_denominators (:677-720): out[X] = 1 / (x_X - z), x_X = g * w_h^bitrev(X), h = 2^log_h, as an

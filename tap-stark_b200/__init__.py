@@ -114,6 +114,7 @@ _SIGNATURES = {
     "ts_alpha_powers": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
     "ts_dot_ext_powers_blocks": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
+    "ts_quotient_values": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
 }

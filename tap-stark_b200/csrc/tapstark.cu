@@ -20,6 +20,7 @@
 #include "ntt_fast.cuh"
 #include "ntt_pm.cuh"
 #include "open.cuh"
+#include "quotient.cuh"
 
 // ------------------------------------------------------------------------------------------------ structs
 struct ts_matrix {
@@ -1677,6 +1678,98 @@ static ef::E4 to_e4(const uint32_t v[4]) {
     for (int i = 0; i < 4; i++) e.c[i] = v[i];
     return e;
 }
+// ---------------------------------------------------------------- quotient values (uni_stark::prove, f3)
+int ts_quotient_values(ts_ctx *c, const ts_matrix *trace_lde, unsigned log_n, unsigned log_quotient_degree,
+                       const uint32_t *program, size_t n_instr, const uint32_t *consts_monty, size_t n_consts,
+                       const uint32_t *public_values_monty, size_t n_public, const uint32_t alpha_monty[4],
+                       ts_matrix **chunks_out) {
+    const unsigned log_m = log_n + log_quotient_degree;
+    const int log_N = log2_strict(trace_lde->rows);
+    if (log_N < 0 || log_m > (unsigned)log_N || log_m > 27)
+        TS_FAIL(c, TS_ERR_ARG, "quotient_values: the quotient domain must fit inside the committed LDE");
+    if (log_quotient_degree > 4 || (1u << log_quotient_degree) > (unsigned)quo::MAX_ZH)
+        TS_FAIL(c, TS_ERR_ARG, "quotient_values: quotient degree too large");
+    // validate the program on the host: a bad index must be an error, not an out-of-bounds access
+    for (size_t pc = 0; pc < n_instr; pc++) {
+        const uint32_t op = program[4 * pc], dst = program[4 * pc + 1];
+        if (op > quo::OP_ASSERT_ZERO) TS_FAIL(c, TS_ERR_ARG, "quotient_values: unknown opcode");
+        if (op != quo::OP_ASSERT_ZERO && dst >= (uint32_t)quo::MAX_REGS) TS_FAIL(c, TS_ERR_ARG, "quotient_values: register index");
+        const int n_ops = (op == quo::OP_ASSERT_ZERO || op == quo::OP_NEG) ? 1 : 2;
+        for (int k = 0; k < n_ops; k++) {
+            const uint32_t code = program[4 * pc + 2 + k], kind = code >> 28, idx = code & 0x0fffffffu;
+            const size_t lim = kind == quo::K_REG ? (size_t)quo::MAX_REGS
+                               : (kind == quo::K_LOCAL || kind == quo::K_NEXT) ? trace_lde->width
+                               : kind == quo::K_PUBLIC ? n_public
+                               : kind == quo::K_CONST ? n_consts
+                               : kind == quo::K_SEL ? (size_t)3 : (size_t)0;
+            if (idx >= lim) TS_FAIL(c, TS_ERR_ARG, "quotient_values: operand out of range");
+        }
+    }
+    const size_t m = (size_t)1 << log_m, n_chunks = (size_t)1 << log_quotient_degree;
+    // program, constants and public values in one device buffer
+    const size_t words = 4 * n_instr + n_consts + n_public + 4;
+    std::vector<uint32_t> host(words, 0);
+    if (n_instr) memcpy(host.data(), program, 16 * n_instr);
+    if (n_consts) memcpy(host.data() + 4 * n_instr, consts_monty, 4 * n_consts);
+    if (n_public) memcpy(host.data() + 4 * n_instr + n_consts, public_values_monty, 4 * n_public);
+    uint32_t *dev = nullptr;
+    TS_CUDA(c, pool_alloc(c, (void **)&dev, words * 4));
+    cudaError_t e = cudaMemcpyAsync(dev, host.data(), words * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // `host` is pageable and dies with this frame
+    if (e != cudaSuccess) {
+        pool_release(c, dev);
+        TS_FAIL(c, TS_ERR_CUDA, std::string("quotient_values upload: ") + cudaGetErrorString(e));
+    }
+    quo::Params p;
+    p.lde = trace_lde->d;
+    p.width = (uint32_t)trace_lde->width;
+    p.log_n = (int)log_n;
+    p.log_m = (int)log_m;
+    p.log_chunks = (int)log_quotient_degree;
+    p.program = dev;
+    p.n_instr = (uint32_t)n_instr;
+    p.consts = dev + 4 * n_instr;
+    p.publics = dev + 4 * n_instr + n_consts;
+    for (int i = 0; i < 4; i++) p.alpha.c[i] = alpha_monty[i];
+    p.rp = root_pows((int)log_m);
+    p.g_monty = TS_GENERATOR_MONTY;
+    p.wn_inv = h_to_monty(bb::cinv(bb::two_adic_generator((int)log_n)));
+    {
+        const uint32_t s_pow_n = bb::cpow(31, (uint64_t)1 << log_n);              // shift^n
+        const uint32_t wq = bb::two_adic_generator((int)log_quotient_degree);      // w_m^n
+        uint32_t x = 1;
+        for (size_t k = 0; k < n_chunks; k++) {
+            const uint32_t z = (uint32_t)(((uint64_t)bb::cmul(s_pow_n, x) + bb::P - 1) % bb::P);
+            p.zh[k] = h_to_monty(z);
+            p.zh_inv[k] = h_to_monty(bb::cinv(z));
+            x = bb::cmul(x, wq);
+        }
+    }
+    int rc = TS_OK;
+    std::vector<ts_matrix *> outs;
+    for (size_t k = 0; k < n_chunks && rc == TS_OK; k++) {
+        ts_matrix *o = nullptr;
+        rc = new_matrix(c, m >> log_quotient_degree, 4, &o);
+        if (rc == TS_OK) {
+            outs.push_back(o);
+            p.out[k] = o->d;
+        }
+    }
+    if (rc == TS_OK) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = quo::quotient_values_kernel;
+        TS_LAUNCH(kfn, (unsigned)((m + 127) / 128), 128, 0, c->stream, p);
+        rc = check_launch(c, "quotient_values_kernel");
+    }
+    pool_release(c, dev);  // stream-ordered
+    if (rc != TS_OK) {
+        for (ts_matrix *o : outs) ts_matrix_free(o);
+        return rc;
+    }
+    for (size_t k = 0; k < n_chunks; k++) chunks_out[k] = outs[k];
+    return TS_OK;
+}
+
 int ts_inv_denoms(ts_ctx *c, unsigned log_h, const uint32_t z_monty[4], ts_matrix **out) {
     if (log_h > 27) TS_FAIL(c, TS_ERR_ARG, "inv_denoms: log_h > 27");
     ts_matrix *o = nullptr;

@@ -258,3 +258,57 @@ def check_pcs_open_verify(ts, ctx, orc, round_shapes, log_blowup, num_queries=6,
         pass
     else:
         raise AssertionError("wrong opened value accepted")
+
+
+# ---- f3: quotient values and the uni-stark prove -> verify round trip ---------------------------------------------
+def check_stark_prove_verify(ts, ctx, orc, air, trace, public_values, log_blowup, num_queries=4, pow_bits=4, tamper=True):
+    """uni_stark::prove on the device path (tap-stark_b200/stark.py) against the oracle: (1) the quotient chunks the
+    constraint-program kernel produces equal the oracle's row-by-row folder evaluation, (2) the proof is accepted by
+    the restated uni_stark::verify, (3) a wrong public value / a tampered opened value is rejected."""
+    from importlib import import_module
+
+    from oracle import stark as OS
+
+    st = import_module(ts.__name__ + ".stark")
+    mmcs = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(log_blowup, num_queries, pow_bits, mmcs))
+    log_n = trace.shape[0].bit_length() - 1
+    log_qd = st.get_log_quotient_degree(air, len(public_values))
+    # (1) quotient chunks
+    dom = pcs.natural_domain_for_degree(trace.shape[0])
+    root, data = pcs.commit([(dom, ts.DeviceMatrix.from_canonical(ctx, trace))])
+    ch = ts.BfChallenger()
+    ch.observe(root)
+    alpha = [int(x) for x in ch.sample()]
+    chunks = st.quotient_values(pcs, data, air, public_values, log_n, log_qd, alpha)
+    lde = orc.pcs_lde_committed(trace, log_blowup)
+    ref = OS.quotient_values(air, public_values, lde, log_n, log_qd, alpha)
+    assert len(chunks) == len(ref) == 1 << log_qd
+    for c_dev, c_ref in zip(chunks, ref):
+        assert np.array_equal(c_dev.to_canonical(), c_ref)
+    # (2) full proof
+    proof = st.prove(pcs, air, ts.BfChallenger(), trace, public_values)
+    assert proof.commitments.trace == root and proof.degree_bits == log_n
+    assert OS.verify(log_blowup, num_queries, pow_bits, air, orc.BfChallenger(), proof, public_values, log_qd)
+    if not tamper:
+        return proof
+    # (3) rejection
+    bad_pis = list(public_values)
+    if bad_pis:
+        bad_pis[-1] = (int(bad_pis[-1]) + 1) % P
+        try:
+            OS.verify(log_blowup, num_queries, pow_bits, air, orc.BfChallenger(), proof, bad_pis, log_qd)
+        except OS.VerificationError as e:
+            assert "OodEvaluationMismatch" in str(e)
+        else:
+            raise AssertionError("wrong public value accepted")
+    v = proof.opened_values.trace_local
+    v[0][0] = (int(v[0][0]) + 1) % P
+    try:
+        OS.verify(log_blowup, num_queries, pow_bits, air, orc.BfChallenger(), proof, public_values, log_qd)
+    except OS.VerificationError:
+        pass
+    else:
+        raise AssertionError("tampered opened value accepted")
+    v[0][0] = (int(v[0][0]) - 1) % P
+    return proof

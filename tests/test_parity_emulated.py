@@ -158,3 +158,36 @@ def test_pcs_open_verify(ts, ctx, orc):
     pc.check_pcs_open_verify(ts, ctx, orc, [[(5, 3, 2)], [(5, 4, 1), (5, 4, 1)]], 2)
     # fri/tests/pcs.rs "many_different": mixed heights in one commit
     pc.check_pcs_open_verify(ts, ctx, orc, [[(4, 2, 1), (6, 3, 1), (3, 2, 1)]], 1, seed=90)
+
+
+def test_stark_fibonacci_prove_verify(ts, ctx, orc):
+    """Config 1's AIR (uni-stark/tests/fib_air.rs: 2^3 rows, log_blowup 2): device quotient values == oracle folder,
+    proof accepted by the restated uni_stark::verify, wrong public value rejected."""
+    import airs
+
+    trace = airs.fibonacci_trace(0, 1, 1 << 3)
+    pc.check_stark_prove_verify(ts, ctx, orc, airs.FibonacciAir(), trace, [0, 1, int(trace[-1, 1])], 2)
+
+
+def test_stark_mul_air_quotient_chunks(ts, ctx, orc):
+    """Degree-3 constraints: quotient degree 2, two chunks on the cosets g*H and g*w_2n*H (split_evals / split_domains)."""
+    import airs
+
+    air = airs.MulAir(degree=3, reps=2)
+    pc.check_stark_prove_verify(ts, ctx, orc, air, airs.mul_trace(air, 1 << 4, 5), [], 2)
+
+
+def test_stark_program_errors(ts, ctx):
+    """A malformed constraint program is an argument error at the ABI, not an out-of-bounds access."""
+    import ctypes as C
+    import numpy as np
+
+    m = ts.DeviceMatrix.from_canonical(ctx, np.zeros((32, 2), dtype=np.uint32))
+    out = (C.c_void_p * 1)()
+    alpha = np.zeros(4, dtype=np.uint32)
+    one = np.zeros(1, dtype=np.uint32)
+    for prog in ([[9, 0, 0, 0]], [[0, 64, 0, 0]], [[0, 0, (1 << 28) | 2, 0]], [[4, 0, (3 << 28) | 0, 0]]):
+        p = np.array(prog, dtype=np.uint32)
+        rc = ctx._L.ts_quotient_values(ctx._h, m._h, 3, 0, p.ctypes.data_as(C.c_void_p), 1, one.ctypes.data_as(C.c_void_p), 0,
+                                       one.ctypes.data_as(C.c_void_p), 0, alpha.ctypes.data_as(C.c_void_p), out)
+        assert rc == 2  # TS_ERR_ARG

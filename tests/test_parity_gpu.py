@@ -321,3 +321,36 @@ def test_pcs_open_verify(ts, ctx, orc):
     pc.check_pcs_open_verify(ts, ctx, orc, [[(5, 3, 2)], [(5, 4, 1), (5, 4, 1)]], 2)
     pc.check_pcs_open_verify(ts, ctx, orc, [[(4, 2, 1), (6, 3, 1), (3, 2, 1)]], 1, seed=90)
     pc.check_pcs_open_verify(ts, ctx, orc, [[(8, 12, 2)], [(8, 4, 1)]], 2, num_queries=16, pow_bits=8, seed=110)
+
+
+def test_stark_fibonacci_config1(ts, ctx, orc):
+    """BASELINE config 1: Fibonacci AIR, 2^10 x 2 trace, log_blowup 2 -- uni_stark::prove on the device path
+    (trace commit -> quotient values kernel -> quotient commit -> open at zeta, zeta*g -> FRI), verified by the
+    restated uni_stark::verify; quotient chunks bit-exact against the oracle's folder evaluation."""
+    import airs
+
+    trace = airs.fibonacci_trace(0, 1, 1 << 10)
+    pc.check_stark_prove_verify(ts, ctx, orc, airs.FibonacciAir(), trace, [0, 1, int(trace[-1, 1])], 2, num_queries=8, pow_bits=8)
+
+
+@pytest.mark.parametrize("degree,log_n", [(3, 6), (5, 7)])
+def test_stark_mul_air(ts, ctx, orc, degree, log_n):
+    """Constraint degree 3 / 5: quotient degree 2 / 4, chunks committed on their own cosets (split_domains)."""
+    import airs
+
+    air = airs.MulAir(degree=degree, reps=3)
+    pc.check_stark_prove_verify(ts, ctx, orc, air, airs.mul_trace(air, 1 << log_n, 11), [], 3 if degree == 5 else 2)
+
+
+def test_stark_program_errors(ts, ctx):
+    import ctypes as C
+
+    m = ts.DeviceMatrix.from_canonical(ctx, np.zeros((32, 2), dtype=np.uint32))
+    out = (C.c_void_p * 1)()
+    alpha = np.zeros(4, dtype=np.uint32)
+    one = np.zeros(1, dtype=np.uint32)
+    for prog in ([[9, 0, 0, 0]], [[0, 64, 0, 0]], [[0, 0, (1 << 28) | 2, 0]], [[4, 0, (3 << 28) | 0, 0]]):
+        p = np.array(prog, dtype=np.uint32)
+        rc = ctx._L.ts_quotient_values(ctx._h, m._h, 3, 0, p.ctypes.data_as(C.c_void_p), 1, one.ctypes.data_as(C.c_void_p), 0,
+                                       one.ctypes.data_as(C.c_void_p), 0, alpha.ctypes.data_as(C.c_void_p), out)
+        assert rc == 2  # TS_ERR_ARG
