@@ -50,6 +50,9 @@ struct ts_ctx {
     // H2D pipeline of the host-buffer entry points: column chunks are copied on copy_stream while the previous
     // chunk's LDE runs on `stream`
     cudaStream_t copy_stream = nullptr;
+    // second compute stream: the leaf hash of column chunk k runs here beside the LDE of chunk k+1 (lde_hash_overlapped)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_side = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_used[2] = {false, false};
     uint32_t *stage[2] = {nullptr, nullptr};
@@ -687,6 +690,52 @@ int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w,
     return TS_OK;
 }
 
+// Device-resident trace -> committed LDE + row hashes, column chunk by column chunk, the Blake3 window of chunk k on
+// a second stream beside the LDE of chunk k+1.  Neither kernel class fills the SM's issue slots on its own (NTT
+// 45-65 %, Blake3 73 %), and an lde_mid CTA (512 threads x 96 registers, 184 KiB) leaves exactly the registers and
+// shared memory of one leaf-hash CTA.  MEASURED NEUTRAL (profiles/r01/README.md): the kernels do co-run, but each slows
+// down by what the other gains (step 51.6 vs 51.9 ms), so this path is opt-in (TS_OVERLAP_HASH=1) and kept as a
+// tested experiment.
+bool overlap_hash_eligible(size_t n, size_t w) {
+    const size_t wc = chunk_cols();
+    return getenv("TS_OVERLAP_HASH") != nullptr && incremental_hash_eligible(w) && log2_strict(n) >= 18 && w >= 2 * wc &&
+           w % wc == 0 && all_digits_fast(log2_strict(n), wc);
+}
+int lde_hash_overlapped(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty, uint32_t *dst,
+                        uint32_t *leaf_digests) {
+    const size_t wc = chunk_cols();
+#ifndef TS_EMULATE
+    if (!c->side_stream) {
+        TS_CUDA(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        TS_CUDA(c, cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    }
+    // the side stream starts after everything already queued on the main stream (the digests' previous users)
+    TS_CUDA(c, cudaEventRecord(c->ev_side, c->stream));
+    TS_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
+#endif
+    int rc = TS_OK;
+    for (size_t col0 = 0; col0 < w && rc == TS_OK; col0 += wc) {
+        rc = lde_committed(c, src + col0, n, wc, b, shift_monty, dst + col0, w, w);
+        if (rc != TS_OK) break;
+#ifndef TS_EMULATE
+        TS_CUDA(c, cudaEventRecord(c->ev_side, c->stream));
+        TS_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
+        cudaStream_t main_stream = c->stream;
+        c->stream = c->side_stream;  // launch + statistics events on the side stream
+        rc = hash_rows_window(c, dst, w, n << b, leaf_digests, (uint32_t)(col0 / 16), (uint32_t)((col0 + wc) / 16));
+        c->stream = main_stream;
+#else
+        rc = hash_rows_window(c, dst, w, n << b, leaf_digests, (uint32_t)(col0 / 16), (uint32_t)((col0 + wc) / 16));
+#endif
+    }
+#ifndef TS_EMULATE
+    // the tree (main stream) waits for the last window; also on errors, so nothing is left running on `dst`
+    cudaEventRecord(c->ev_side, c->side_stream);
+    cudaStreamWaitEvent(c->stream, c->ev_side, 0);
+#endif
+    return rc;
+}
+
 int new_matrix(ts_ctx *c, size_t rows, size_t width, ts_matrix **out) {
     ts_matrix *m = new ts_matrix{c, nullptr, rows, width, true};
     cudaError_t e = pool_alloc(c, (void **)&m->d, std::max<size_t>(rows * width, 1) * 4);
@@ -1046,6 +1095,11 @@ void ts_ctx_destroy(ts_ctx *c) {
     cudaFree(c->stage[0]);
     cudaFree(c->stage[1]);
 #ifndef TS_EMULATE
+    if (c->side_stream) {
+        cudaStreamSynchronize(c->side_stream);
+        cudaEventDestroy(c->ev_side);
+        cudaStreamDestroy(c->side_stream);
+    }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int s = 0; s < 2; s++) {
@@ -1500,6 +1554,17 @@ int ts_pcs_commit(ts_ctx *c, ts_matrix *const *evals, const uint32_t *domain_shi
         }
         const uint32_t shift = h_to_monty(bb::cmul(31, bb::cinv(dshift)));
         ts_matrix *lde = nullptr;
+        if (n == 1 && log2_strict(evals[i]->rows) >= 0 && overlap_hash_eligible(evals[i]->rows, evals[i]->width)) {
+            rc = new_matrix(c, evals[i]->rows << log_blowup, evals[i]->width, &lde);
+            if (rc != TS_OK) break;
+            const ts_matrix *ev = evals[i];
+            const std::function<int(uint32_t *)> fill = [&](uint32_t *leaf_digests) {
+                return lde_hash_overlapped(c, ev->d, ev->rows, ev->width, log_blowup, shift, lde->d, leaf_digests);
+            };
+            rc = mmcs_commit(c, &lde, 1, layout, 1, root, out, true, &fill);
+            if (rc != TS_OK) ts_matrix_free(lde);
+            return rc;
+        }
         rc = ts_coset_lde_batch(c, evals[i], log_blowup, shift, 0, &lde);
         if (rc == TS_OK) ldes.push_back(lde);
     }

@@ -75,6 +75,24 @@ def test_pcs_commit_host_pipelined(ts, ctx, orc, monkeypatch, chunk, width):
     assert root == orc.mmcs_commit([lde]).root
 
 
+def test_pcs_commit_overlapped_hash(ts, ctx, orc, monkeypatch):
+    """Device-resident commit of one wide matrix: LDE by column chunks with the Blake3 window of chunk k issued on a
+    second stream beside the LDE of chunk k+1 (lde_hash_overlapped); same root and LDE as the oracle."""
+    import numpy as np
+
+    monkeypatch.setenv("TS_CHUNK_COLS", "16")
+    monkeypatch.setenv("TS_OVERLAP_HASH", "1")  # opt-in: measured neutral on the B200 (profiles/r01/README.md)
+    ev = pc.rand_mat(33, 1 << 18, 48)
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
+    ctx.reset_stats()
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(1 << 18), ts.DeviceMatrix.from_canonical(ctx, ev))])
+    assert ctx.stats()["hash_leaves"]["launches"] == 3
+    lde = orc.pcs_lde_committed(ev, 1)
+    assert np.array_equal(mm.get_matrices(data)[0].to_canonical(), lde)
+    assert root == orc.mmcs_commit([lde]).root
+
+
 def test_lde_other_shift(ts, ctx, orc):
     pc.check_lde(ts, ctx, orc, 6, 4, 2, shift=1)
     pc.check_lde(ts, ctx, orc, 12, 2, 1, shift=pow(31, 5, pc.P))
