@@ -126,6 +126,9 @@ size_t ts_tree_num_matrices(const ts_tree *t);
 ts_matrix *ts_tree_matrix(const ts_tree *t, size_t i); /* BFMmcs::get_matrices */
 size_t ts_tree_depth(const ts_tree *t);                /* siblings in an opening */
 size_t ts_tree_max_height(const ts_tree *t);           /* BFMmcs::get_max_height */
+/* the 32-byte root, device to device on the context's stream (no host synchronisation): a rank's sub-root goes
+ * straight into the all-gather buffer; ts_mmcs_commit with root == NULL skips the host copy of the root. */
+int ts_tree_root_copy(ts_ctx *ctx, const ts_tree *t, uint8_t *dst_device);
 /* BFMmcs::open_batch(query_index): rows_out receives every matrix's opened row (Montgomery) concatenated
  * in caller order (sum of widths u32); path_out receives depth x 32 bytes. */
 int ts_mmcs_open_batch(ts_ctx *ctx, const ts_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out);

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "ts_alpha_powers": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
     "ts_dot_ext_powers_blocks": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
+    "ts_tree_root_copy": (C.c_int, [_vp, _vp, _vp]),
     "ts_quotient_values": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
@@ -355,6 +356,10 @@ class ProverData:
         self.ctx.check(self.ctx._L.ts_tree_layer(self.ctx._h, self._h, i, _ptr(out), C.byref(n)), "tree_layer")
         return out
 
+    def root_to_device(self, dst_ptr: int) -> None:
+        """Copies the 32-byte root to device memory at dst_ptr on the context's stream (no host synchronisation)."""
+        self.ctx.check(self.ctx._L.ts_tree_root_copy(self.ctx._h, self._h, C.c_void_p(dst_ptr)), "tree_root_copy")
+
     def free(self):
         if self._h:
             self.ctx._L.ts_tree_free(self._h)
@@ -374,14 +379,16 @@ class Blake3MerkleMmcs:
     def __init__(self, ctx: Context, layout: int = LAYOUT_P3_INJECT):
         self.ctx, self.layout = ctx, layout
 
-    def commit(self, inputs: Sequence[DeviceMatrix], take_ownership: bool = False) -> Tuple[bytes, ProverData]:
+    def commit(self, inputs: Sequence[DeviceMatrix], take_ownership: bool = False, host_root: bool = True):
+        """host_root=False: the root stays on the device (no synchronisation); returns (None, ProverData) and the
+        caller fetches it with ProverData.root_to_device (multi-GPU sub-roots go straight into the all-gather)."""
         k = len(inputs)
         arr = (C.c_void_p * k)(*[m._h for m in inputs])
         root = (C.c_uint8 * 32)()
         h = C.c_void_p()
-        self.ctx.check(self.ctx._L.ts_mmcs_commit(self.ctx._h, arr, k, self.layout, int(take_ownership), root, C.byref(h)),
-                       "mmcs_commit")
-        return bytes(root), ProverData(self.ctx, h, inputs, take_ownership)
+        self.ctx.check(self.ctx._L.ts_mmcs_commit(self.ctx._h, arr, k, self.layout, int(take_ownership),
+                                                  root if host_root else None, C.byref(h)), "mmcs_commit")
+        return (bytes(root) if host_root else None), ProverData(self.ctx, h, inputs, take_ownership)
 
     def commit_matrix(self, m: DeviceMatrix) -> Tuple[bytes, ProverData]:
         return self.commit([m])

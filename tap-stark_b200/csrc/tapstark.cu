@@ -1293,6 +1293,10 @@ size_t ts_tree_num_matrices(const ts_tree *t) { return t->mats.size(); }
 ts_matrix *ts_tree_matrix(const ts_tree *t, size_t i) { return i < t->mats.size() ? t->mats[i] : nullptr; }
 size_t ts_tree_depth(const ts_tree *t) { return t->lmax; }
 size_t ts_tree_max_height(const ts_tree *t) { return t->hmax; }
+int ts_tree_root_copy(ts_ctx *c, const ts_tree *t, uint8_t *dst_device) {
+    TS_CUDA(c, cudaMemcpyAsync(dst_device, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToDevice, c->stream));
+    return TS_OK;
+}
 int ts_mmcs_open_batch(ts_ctx *c, const ts_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out) {
     if (index >= t->hmax) TS_FAIL(c, TS_ERR_ARG, "open_batch: index out of range");
     size_t o = 0;

@@ -60,20 +60,24 @@ class ShardedProver:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
-    def combine_roots(self, sub_root: bytes) -> bytes:
-        """all-gather the G sub-roots and hash the top log2(G) levels (parent = Blake3(left || right))."""
+    def combine_roots(self, data) -> bytes:
+        """all-gather the G sub-roots (device to device: the sub-root never visits the host on its own) and hash the
+        top log2(G) levels (parent = Blake3(left || right)) on every host: one device->host read per call."""
         torch, dist = self.torch, self.dist
-        mine = torch.frombuffer(bytearray(sub_root), dtype=torch.uint8).to(self.device)
-        outs = [torch.empty(32, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
-        dist.all_gather(outs, mine)
-        layer = [bytes(o.cpu().numpy().tobytes()) for o in outs]
+        G = self.world
+        buf = torch.empty((G + 1) * 32, dtype=torch.uint8, device=self.device)
+        mine = buf[G * 32 :]
+        data.root_to_device(mine.data_ptr())
+        dist.all_gather_into_tensor(buf[: G * 32], mine)
+        flat = buf[: G * 32].cpu().numpy()
+        layer = [flat[32 * i : 32 * i + 32].tobytes() for i in range(G)]
         L = self.ctx._L
         while len(layer) > 1:
             nxt = []
             for i in range(0, len(layer), 2):
-                buf = layer[i] + layer[i + 1]
+                pair = layer[i] + layer[i + 1]
                 out = (C.c_uint8 * 32)()
-                L.ts_blake3_host(C.c_char_p(buf), 64, out)
+                L.ts_blake3_host(C.c_char_p(pair), 64, out)
                 nxt.append(bytes(out))
             layer = nxt
         return layer[0]
@@ -162,8 +166,8 @@ class ShardedProver:
         for s_ in range(G):
             for c in range(C_):
                 blocks.append(self._wrap(recv[c][s_], Nl, wc))
-        sub_root, data = self.mmcs.commit(blocks)
-        root = self.combine_roots(sub_root)
+        _, data = self.mmcs.commit(blocks, host_root=False)
+        root = self.combine_roots(data)
         marks.append(self._mark())  # leaf hashes, sub-tree, sub-root all-gather
         ch = ts.BfChallenger()
         ch.observe(root)
@@ -212,8 +216,8 @@ class ShardedProver:
             h_g, h_l = len_g // 2, local // 2
             if len_g > self.REPLICATE_BELOW and h_l >= 256 and h_l * G == h_g:
                 leaves = self._wrap(cur_t, h_l, 8)
-                sub, data = self.mmcs.commit([leaves])
-                root = self.combine_roots(sub)
+                _, data = self.mmcs.commit([leaves], host_root=False)
+                root = self.combine_roots(data)
                 data.free()
                 commits.append(root)
                 ch.observe(root)
@@ -225,9 +229,8 @@ class ShardedProver:
                 cur_t, len_g, local = out_t, h_g, h_l
                 continue
             # small layer: gather it everywhere and finish replicated (no further communication)
-            parts = [torch.empty_like(cur_t) for _ in range(G)]
-            dist.all_gather(parts, cur_t)
-            full_t = torch.cat(parts, dim=0).contiguous()
+            full_t = torch.empty((len_g, 4), dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(full_t.view(-1), cur_t.contiguous().view(-1))
             res = ts.bf_commit_phase(self.cfg, [self._wrap(full_t, len_g, 4)], ch, keep_data=False)
             commits += res.commits
             return commits, res.final_poly.tolist()
