@@ -233,6 +233,21 @@ int ts_matrix_zero(ts_ctx *ctx, ts_matrix *m);
 /* LDE written into caller-owned memory (e.g. the send buffer of the all-to-all). */
 int ts_coset_lde_batch_into(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
                             ts_matrix *out);
+/* Fused LDE + re-shard: the committed LDE of this rank's columns with every output row written by the LAST butterfly
+ * pass straight to the rank that owns its row range -- committed row r goes to owner_ptrs[r / (N / n_owners)] at local
+ * row r % (N / n_owners), dst_pitch words per row, columns [0, width).  Remote owners are peer-mapped device memory
+ * (ts_ipc_open), i.e. the stores travel over NVLink as part of the kernel and no all-to-all follows; the caller
+ * orders "all ranks have written" before anyone reads (one tiny collective on the stream).  Needs the position-major
+ * two-digit path (rows >= 2^18, width % 4 == 0); otherwise TS_ERR_ARG and the caller uses ts_coset_lde_batch_into +
+ * all-to-all. */
+int ts_coset_lde_batch_scatter(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
+                               uint32_t *const *owner_ptrs, size_t n_owners, size_t dst_pitch);
+/* device allocations shareable across the processes of one node, and their CUDA IPC handles (64 bytes) */
+int ts_device_malloc(ts_ctx *ctx, size_t bytes, void **out);
+int ts_device_free(ts_ctx *ctx, void *p);
+int ts_ipc_get_handle(ts_ctx *ctx, void *dev_ptr, uint8_t handle[64]);
+int ts_ipc_open(ts_ctx *ctx, const uint8_t handle[64], void **out);
+int ts_ipc_close(ts_ctx *ctx, void *p);
 /* alpha^0 .. alpha^(count-1) (+16 zero entries) as a device matrix, computed once per opening */
 int ts_alpha_powers(ts_ctx *ctx, const uint32_t alpha_monty[4], size_t count, ts_matrix **out);
 /* acc (+)= sum_c alpha^(first_power + c) * m[:, c]; a row shard whose columns arrive as several blocks calls it

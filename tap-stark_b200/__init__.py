@@ -115,6 +115,12 @@ _SIGNATURES = {
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
     "ts_dot_ext_powers_blocks": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
     "ts_tree_root_copy": (C.c_int, [_vp, _vp, _vp]),
+    "ts_coset_lde_batch_scatter": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint32, _vp, C.c_size_t, C.c_size_t]),
+    "ts_device_malloc": (C.c_int, [_vp, C.c_size_t, _vpp]),
+    "ts_device_free": (C.c_int, [_vp, _vp]),
+    "ts_ipc_get_handle": (C.c_int, [_vp, _vp, _vp]),
+    "ts_ipc_open": (C.c_int, [_vp, _vp, _vpp]),
+    "ts_ipc_close": (C.c_int, [_vp, _vp]),
     "ts_quotient_values": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),

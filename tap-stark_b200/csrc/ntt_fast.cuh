@@ -276,6 +276,11 @@ struct FastPassParams {
     uint32_t n_col_slices;
     int tw_shift;  // big_log - (lo_bits + D)
     FastTables t;
+    // peer_log_rows >= 0 (last forward pass of a column-sharded LDE, ntt_pm only): output row r is written to
+    // peer[r >> peer_log_rows] at row r & (2^peer_log_rows - 1), dst_pitch words per row -- the owner of that row range;
+    // remote entries are peer-mapped device memory (NVLink stores), so the re-shard needs no separate all-to-all
+    uint32_t *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int peer_log_rows = -1;
 };
 #ifndef TS_PASS_MINBLOCKS
 #define TS_PASS_MINBLOCKS 2

@@ -328,6 +328,25 @@ TS_D void store_tile(const uint4 *tile, uint32_t *dst, size_t row_base, size_t r
     }
 }
 
+// store of the last forward pass of a column-sharded LDE: every row goes to the rank that owns its row range.  Lanes walk
+// (quad, position) in order, so with contiguous rows a warp writes one contiguous 512-byte run -- full NVLink packets.
+template <int D, int NT, int NQv = dnq(D)>
+TS_D void store_tile_peers(const uint4 *tile, const nttf::FastPassParams &p, size_t row_base, size_t row_stride, uint32_t col0,
+                           int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int TOTAL = G::L * G::NQ;
+    const size_t mask = ((size_t)1 << p.peer_log_rows) - 1;
+    for (int it = tid; it < TOTAL; it += NT) {
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        const uint32_t col = col0 + 4 * h;
+        if (col < p.ncols) {
+            const size_t row = row_base + (size_t)q * row_stride;
+            uint32_t *base = p.peer[row >> p.peer_log_rows];
+            *reinterpret_cast<uint4 *>(base + (row & mask) * p.dst_pitch + col) = tile[hx<D>(h) ^ sigma(q)];
+        }
+    }
+}
+
 // ---- rounds fused with tile I/O ------------------------------------------------------------------------------
 // The first DIF round can take its operands straight from global memory and the last one can write its results
 // straight back: two of the five shared-memory round trips and two of the five barriers of a tile disappear.
@@ -459,7 +478,11 @@ __global__ void __launch_bounds__(PM_PASS_NT, TS_PM_PASS_MINBLOCKS) ntt_pass_pm_
     __syncthreads();
     dif_r3<D, INV, false, PM_PASS_NT>(tile, p.t, nullptr, tid);
     __syncthreads();
-    if (p.lo_bits > 0)
+    if (p.peer_log_rows >= 0) {  // scatter to the row owners (ts_coset_lde_batch_scatter); only the contiguous last digit
+        dif_r4<D, INV, false, PM_PASS_NT>(tile, p.t, 0, 0, tid);
+        __syncthreads();
+        store_tile_peers<D, PM_PASS_NT>(tile, p, row_base, row_stride, col0, tid);
+    } else if (p.lo_bits > 0)
         dif_r4_st<D, INV, true, PM_PASS_NT>(tile, p.dst, row_base, row_stride, p.dst_pitch, p.dst_slice, p.ncols, col0, p.t, lo,
                                             p.tw_shift, tid);
     else

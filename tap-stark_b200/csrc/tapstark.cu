@@ -309,9 +309,13 @@ int launch_pass_fast(ts_ctx *c, bool inverse, const nttf::FastPassParams &p, siz
 
 // w columns are transformed; src_pitch/dst_pitch (0 = w) are the row strides when src/dst are column windows of
 // wider matrices (fast path only)
+struct PeerDst {  // row owners of a column-sharded LDE (ts_coset_lde_batch_scatter)
+    uint32_t *ptr[8];
+    int n;
+};
 int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, size_t w, int d, int lo_bits,
                 int hi_bits, bool has_scale, uint2 scale, size_t src_pitch = 0, size_t dst_pitch = 0,
-                size_t src_slice = 0, size_t dst_slice = 0) {
+                size_t src_slice = 0, size_t dst_slice = 0, const PeerDst *peers = nullptr) {
     if (!src_pitch) src_pitch = w;
     if (!dst_pitch) dst_pitch = w;
     if ((src_slice || dst_slice) && !(use_pm() && !has_scale && fast_shape(d, w)))
@@ -331,6 +335,12 @@ int launch_pass(ts_ctx *c, bool inverse, const uint32_t *src, uint32_t *dst, siz
         fp.n_col_slices = (uint32_t)((w + K - 1) / K);
         fp.t = fast_tables(c);
         fp.tw_shift = lo_bits > 0 ? c->big_log - (lo_bits + d) : 0;
+        if (peers) {
+            if (!use_pm() || use_persistent() || lo_bits != 0 || inverse)
+                TS_FAIL(c, TS_ERR_ARG, "lde scatter: needs the position-major last forward pass");
+            for (int i = 0; i < peers->n; i++) fp.peer[i] = peers->ptr[i];
+            fp.peer_log_rows = hi_bits + d - log2_strict((size_t)peers->n);  // rows of the output / peers
+        }
         const size_t blocks = ((size_t)1 << (hi_bits + lo_bits)) * fp.n_col_slices;
         switch (d) {
             case 9: return launch_pass_fast<9>(c, inverse, fp, blocks);
@@ -452,13 +462,14 @@ bool all_digits_fast(int m, size_t w) {
 
 // windows: src is n x w with row stride src_pitch, dst is (n<<b) x w with row stride dst_pitch (0 = w)
 int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty,
-                  uint32_t *dst, size_t src_pitch = 0, size_t dst_pitch = 0) {
+                  uint32_t *dst, size_t src_pitch = 0, size_t dst_pitch = 0, const PeerDst *peers = nullptr) {
     if (!src_pitch) src_pitch = w;
     if (!dst_pitch) dst_pitch = w;
     const int m = log2_strict(n);
     if (m < 0 || w == 0 || m + (int)b > 27) TS_FAIL(c, TS_ERR_ARG, "lde: rows must be a power of two, rows<<added_bits <= 2^27");
     if ((src_pitch != w || dst_pitch != w) && !all_digits_fast(m, w))
         TS_FAIL(c, TS_ERR_ARG, "column windows need the fast NTT path");
+    if (peers && m < 2) TS_FAIL(c, TS_ERR_ARG, "lde scatter: shape not on the blocked position-major path");
     if (m == 0) {
         KScope ks(c, TS_K_MISC);
         auto kfn = ntt::broadcast_row_kernel;
@@ -472,6 +483,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
     // Blocked intermediates ([col/8][row][8], see ntt_pm.cuh word_off): only the first read and the last write
     // of a multi-digit LDE use the caller's row-major matrices.
     const bool blocked = D > 1 && use_pm() && all_digits_fast(m, w) && getenv("TS_NO_BLOCKED") == nullptr;
+    if (peers && !blocked) TS_FAIL(c, TS_ERR_ARG, "lde scatter: shape not on the blocked position-major path");
     const size_t w8 = (w + 7) & ~(size_t)7, N = n << b;
     const size_t s_slice = blocked ? n * 8 : 0, i_slice = blocked ? N * 8 : 0;
     uint32_t *inter = nullptr;  // blocked N x w intermediate between lde_mid and the last forward pass
@@ -586,7 +598,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         const bool last = i + 2 == D;
         if (blocked)
             rc = launch_pass(c, false, inter, last ? dst : inter, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), w,
-                             last ? dst_pitch : w, i_slice, last ? 0 : i_slice);
+                             last ? dst_pitch : w, i_slice, last ? 0 : i_slice, last ? peers : nullptr);
         else
             rc = launch_pass(c, false, dst, dst, w, dg[i], lo_bits, hi_bits, false, make_uint2(0, 0), dst_pitch, dst_pitch);
         used += dg[i];
@@ -1942,6 +1954,60 @@ int ts_coset_lde_batch_into(ts_ctx *c, const ts_matrix *evals, unsigned added_bi
     if (out->rows != (evals->rows << added_bits) || out->width != evals->width)
         TS_FAIL(c, TS_ERR_ARG, "coset_lde_batch_into: out must be (rows<<added_bits) x width");
     return lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, out->d);
+}
+int ts_coset_lde_batch_scatter(ts_ctx *c, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
+                               uint32_t *const *owner_ptrs, size_t n_owners, size_t dst_pitch) {
+    if (n_owners < 1 || n_owners > 8 || (n_owners & (n_owners - 1))) TS_FAIL(c, TS_ERR_ARG, "lde scatter: 1, 2, 4 or 8 owners");
+    if (dst_pitch < evals->width || (dst_pitch & 3)) TS_FAIL(c, TS_ERR_ARG, "lde scatter: bad pitch");
+    PeerDst pd;
+    pd.n = (int)n_owners;
+    for (size_t i = 0; i < 8; i++) pd.ptr[i] = i < n_owners ? owner_ptrs[i] : nullptr;
+    return lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, nullptr, 0, dst_pitch, &pd);
+}
+// CUDA IPC plumbing for the peer-mapped receive buffers (one process per GPU)
+int ts_device_malloc(ts_ctx *c, size_t bytes, void **out) {
+    TS_CUDA(c, cudaMalloc(out, bytes));
+    return TS_OK;
+}
+int ts_device_free(ts_ctx *c, void *p) {
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    TS_CUDA(c, cudaFree(p));
+    return TS_OK;
+}
+int ts_ipc_get_handle(ts_ctx *c, void *dev_ptr, uint8_t handle[64]) {
+#ifndef TS_EMULATE
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    TS_CUDA(c, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return TS_OK;
+#else
+    (void)dev_ptr;
+    (void)handle;
+    TS_FAIL(c, TS_ERR_ARG, "ipc: not available in the emulated build");
+#endif
+}
+int ts_ipc_open(ts_ctx *c, const uint8_t handle[64], void **out) {
+#ifndef TS_EMULATE
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    TS_CUDA(c, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return TS_OK;
+#else
+    (void)handle;
+    (void)out;
+    TS_FAIL(c, TS_ERR_ARG, "ipc: not available in the emulated build");
+#endif
+}
+int ts_ipc_close(ts_ctx *c, void *p) {
+#ifndef TS_EMULATE
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    TS_CUDA(c, cudaIpcCloseMemHandle(p));
+    return TS_OK;
+#else
+    (void)p;
+    TS_FAIL(c, TS_ERR_ARG, "ipc: not available in the emulated build");
+#endif
 }
 int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev) {

@@ -60,6 +60,56 @@ class ShardedProver:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
+    # ---- peer-mapped receive buffers: the LDE's last pass stores every row at its owner (NVLink), no all-to-all ------
+    def _p2p_setup(self, N: int, wc: int, n_chunks: int):
+        """Allocates this rank's receive buffers ([G, N/G, wc] per chunk), exchanges their CUDA IPC handles and maps every
+        peer's buffers.  Returns per-chunk (own base pointer, owner pointer table) or None when the fused path is
+        unavailable (CPU/gloo, TS_P2P=0, IPC or peer access refused): the caller then uses NCCL all-to-all.  Collective."""
+        import os
+
+        key = (N, wc, n_chunks)
+        cache = self.__dict__.setdefault("_p2p_cache", {})
+        if key in cache:
+            return cache[key]
+        torch, dist, ctx, L, G, r = self.torch, self.dist, self.ctx, self.ctx._L, self.world, self.rank
+        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("TS_P2P", "1") != "0" and G <= 8
+        Nl = N // G
+        bases, handles = [], []
+        if ok:
+            for _ in range(n_chunks):
+                p_ = C.c_void_p()
+                h_ = (C.c_uint8 * 64)()
+                if L.ts_device_malloc(ctx._h, G * Nl * wc * 4, C.byref(p_)) != 0 or L.ts_ipc_get_handle(ctx._h, p_, h_) != 0:
+                    ok = False
+                    break
+                bases.append(p_.value)
+                handles.append(bytes(h_))
+        gathered = [None] * G
+        dist.all_gather_object(gathered, handles if ok else None)
+        ok = ok and all(g is not None for g in gathered)
+        plan = None
+        if ok:
+            plan = []
+            for c in range(n_chunks):
+                owners = (C.c_void_p * G)()
+                for d in range(G):
+                    if d == r:
+                        base_d = bases[c]
+                    else:
+                        q_ = C.c_void_p()
+                        if L.ts_ipc_open(ctx._h, C.c_char_p(gathered[d][c]), C.byref(q_)) != 0:
+                            ok = False
+                            break
+                        base_d = q_.value
+                    owners[d] = base_d + r * Nl * wc * 4  # my block inside rank d's [G, Nl, wc] buffer
+                if not ok:
+                    break
+                plan.append((bases[c], owners))
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # everyone or no one; also: all mappings exist before the first store
+        cache[key] = plan if int(flag.item()) == 1 else None
+        return cache[key]
+
     def combine_roots(self, data) -> bytes:
         """all-gather the G sub-roots (device to device: the sub-root never visits the host on its own) and hash the
         top log2(G) levels (parent = Blake3(left || right)) on every host: one device->host read per call."""
@@ -88,8 +138,11 @@ class ShardedProver:
     def _chunks(self, wl: int) -> int:
         """column chunks per rank: the LDE of chunk c+1 overlaps the all-to-all of chunk c (NCCL runs on its own
         stream).  Chunk widths stay powers of two >= 8 so the received blocks feed the fast leaf kernel."""
+        import os
+
+        cmax = int(os.environ.get("TS_SHARD_CHUNKS", "4"))  # measurement hook
         c = 1
-        while c < 4 and wl % (2 * c) == 0 and wl // (2 * c) >= 8 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
+        while c < cmax and wl % (2 * c) == 0 and wl // (2 * c) >= 8 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
             c *= 2
         return c if self.world > 1 else 1
 
@@ -139,6 +192,7 @@ class ShardedProver:
                     e_.record(self._copy_stream)
                     d_.record_stream(main)
                     staged.append((d_, e_))
+        plan = self._p2p_setup(N, wc, C_) if (G > 1 and n >= 1 << 18 and wc % 4 == 0) else None
         for c in range(C_):
             if host_panels is not None:
                 src_t, ev_ = staged[c]
@@ -146,6 +200,11 @@ class ShardedProver:
             else:
                 src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
             ev = self._wrap(src_t, n, wc)
+            if plan is not None:
+                # fused LDE + re-shard: the last butterfly pass writes each row range into its owner's buffer
+                ctx.check(L.ts_coset_lde_batch_scatter(ctx._h, ev._h, b, gen, plan[c][1], G, wc), "coset_lde_batch_scatter")
+                keep.append(src_t)
+                continue
             lde_t = torch.empty((N, wc), dtype=torch.int32, device=self.device)
             lde = self._wrap(lde_t, N, wc)
             ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
@@ -159,13 +218,21 @@ class ShardedProver:
             keep.append((lde_t, src_t))
         for w_ in works:
             w_.wait()
+        if plan is not None:
+            # every rank's stores into my buffers are complete once all ranks have passed this point in stream order
+            if not hasattr(self, "_p2p_flag"):
+                self._p2p_flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+            dist.all_reduce(self._p2p_flag)
         del keep
         marks.append(self._mark())  # LDE + re-shard done
         # global column order: rank-major, then chunk
         blocks = []
         for s_ in range(G):
             for c in range(C_):
-                blocks.append(self._wrap(recv[c][s_], Nl, wc))
+                if plan is not None:
+                    blocks.append(ts.DeviceMatrix.wrap_device(ctx, plan[c][0] + s_ * Nl * wc * 4, Nl, wc))
+                else:
+                    blocks.append(self._wrap(recv[c][s_], Nl, wc))
         _, data = self.mmcs.commit(blocks, host_root=False)
         root = self.combine_roots(data)
         marks.append(self._mark())  # leaf hashes, sub-tree, sub-root all-gather
