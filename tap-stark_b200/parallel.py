@@ -64,7 +64,8 @@ class ShardedProver:
     def _p2p_setup(self, N: int, wc: int, n_chunks: int):
         """Allocates this rank's receive buffers ([G, N/G, wc] per chunk), exchanges their CUDA IPC handles and maps every
         peer's buffers.  Returns per-chunk (own base pointer, owner pointer table) or None when the fused path is
-        unavailable (CPU/gloo, TS_P2P=0, IPC or peer access refused): the caller then uses NCCL all-to-all.  Collective."""
+        unavailable or not requested (CPU/gloo, TS_P2P != 1, IPC or peer access refused): the caller then uses the NCCL
+        all-to-all overlapped with the next chunk's LDE, which is the faster form on NVSwitch B200s.  Collective."""
         import os
 
         key = (N, wc, n_chunks)
@@ -72,7 +73,8 @@ class ShardedProver:
         if key in cache:
             return cache[key]
         torch, dist, ctx, L, G, r = self.torch, self.dist, self.ctx, self.ctx._L, self.world, self.rank
-        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("TS_P2P", "1") != "0" and G <= 8
+        # opt-in: measured SLOWER than the chunk-overlapped NCCL all-to-all on 2/4/8 B200s (profiles/r01/README.md)
+        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("TS_P2P", "0") == "1" and G <= 8
         Nl = N // G
         bases, handles = [], []
         if ok:

@@ -1,6 +1,6 @@
 """The N>1 path on real GPUs (needs >= 2 devices; skipped otherwise): NCCL ranks of tap-stark_b200/parallel.py with the
-fused LDE + re-shard (last butterfly pass storing into peer-mapped buffers) and, with TS_P2P=0, the NCCL all-to-all
-form; both must reproduce the single-process oracle transcript bit for bit."""
+default NCCL all-to-all re-shard and, with TS_P2P=1, the fused LDE + re-shard (last butterfly pass storing into
+peer-mapped buffers); both must reproduce the single-process oracle transcript bit for bit."""
 import json
 import os
 import subprocess
