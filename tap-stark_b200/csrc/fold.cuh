@@ -159,8 +159,9 @@ TS_D uint64_t fold64(uint64_t t) {
 // below p 2^32 by a min on the high word every two products and Montgomery-reduced once per row.
 // apow must be padded with zeros to a multiple of 16 entries.
 constexpr int DOT_FAST_WARPS = 8;
+constexpr size_t DOT_SMEM_BYTES = (size_t)DOT_FAST_WARPS * 1024 * 4;  // 4 KiB transpose buffer per warp
 #ifndef TS_DOT_MINBLOCKS
-#define TS_DOT_MINBLOCKS 4
+#define TS_DOT_MINBLOCKS 3
 #endif
 // Several column blocks of EQUAL power-of-two width (what a rank holds after the all-to-all) are read as one row:
 // word cw of the row lives in block cw >> log_seg_w (same convention as b3::FastSegs).
@@ -176,19 +177,21 @@ __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_row
                                                                           uint4 *__restrict__ out, int accumulate) {
     TS_DYN_SMEM(uint32_t, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *ws = sm + warp * 512;
+    uint32_t *ws = sm + warp * 1024;
     const size_t row0 = ((size_t)blockIdx.x * DOT_FAST_WARPS + warp) * 32;
     if (row0 >= rows) return;  // warp-uniform
-    const uint32_t total_blocks = (width + 15u) / 16u;
-    const uint32_t sub = lane & 3, r0 = lane >> 2;
-    uint4 pf[4];
+    // one iteration = 32 columns: 8 lanes cover 128 contiguous bytes of a row (4 rows per LDG.128), 8 loads per lane
+    // in flight one iteration ahead -- 128-byte DRAM bursts and twice the bytes in flight of the 64-byte version
+    const uint32_t total_iters = (width + 31u) / 32u;
+    const uint32_t sub = lane & 7, r0 = lane >> 3;
+    uint4 pf[8];
     // 64-bit running sums, kept below p * 2^32 (the Montgomery reduction's input range) by one conditional subtraction
     // of p * 2^32 -- a min on the high word -- after every two products (2 p^2 + p 2^32 < 2 p 2^32 < 2^64)
     uint64_t acc[4] = {0, 0, 0, 0};
-#define TS_DOT_FETCH(blk_)                                                                           \
+#define TS_DOT_FETCH(it_)                                                                            \
     TS_UNROLL                                                                                        \
-    for (int k = 0; k < 4; k++) {                                                                    \
-        const uint32_t row = r0 + 8 * k, cw = 16u * (blk_) + 4u * sub;                               \
+    for (int k = 0; k < 8; k++) {                                                                    \
+        const uint32_t row = r0 + 4 * k, cw = 32u * (it_) + 4u * sub;                                \
         const uint32_t sgi = sg.n > 1 ? (cw >> sg.log_seg_w) : 0u;                                   \
         const uint32_t off = sg.n > 1 ? (cw & (sg.seg_w - 1u)) : cw;                                 \
         pf[k] = (row0 + row < rows && cw < width)                                                    \
@@ -196,29 +199,34 @@ __global__ void __launch_bounds__(DOT_FAST_WARPS * 32, TS_DOT_MINBLOCKS) dot_row
                     : make_uint4(0, 0, 0, 0);                                                        \
     }
     TS_DOT_FETCH(0u)
-    for (uint32_t blk = 0; blk < total_blocks; blk++) {
+    for (uint32_t it = 0; it < total_iters; it++) {
         TS_UNROLL
-        for (int k = 0; k < 4; k++) {
-            const uint32_t row = r0 + 8 * k;
-            *reinterpret_cast<uint4 *>(ws + row * 16 + 4 * (sub ^ ((row >> 1) & 3u))) = pf[k];
+        for (int k = 0; k < 8; k++) {
+            const uint32_t row = r0 + 4 * k;
+            *reinterpret_cast<uint4 *>(ws + row * 32 + 4 * (sub ^ (row & 7u))) = pf[k];
         }
         __syncwarp();
-        if (blk + 1 < total_blocks) { TS_DOT_FETCH(blk + 1) }
-        uint32_t v[16];
+        if (it + 1 < total_iters) { TS_DOT_FETCH(it + 1) }
         TS_UNROLL
-        for (int j = 0; j < 4; j++) {
-            const uint4 t = *reinterpret_cast<const uint4 *>(ws + lane * 16 + 4 * ((uint32_t)j ^ ((lane >> 1) & 3u)));
-            v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        for (int half = 0; half < 2; half++) {
+            const uint32_t c0 = 32u * it + 16u * half;
+            if (c0 >= width) break;  // warp-uniform: apow is padded to 16, not 32
+            uint32_t v[16];
+            TS_UNROLL
+            for (int j = 0; j < 4; j++) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(ws + lane * 32 + 4 * ((uint32_t)(4 * half + j) ^ (lane & 7u)));
+                v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            TS_UNROLL
+            for (int i = 0; i < 16; i += 2) {
+                const uint4 a0 = __ldg(apow + c0 + i), a1 = __ldg(apow + c0 + i + 1);
+                acc[0] = fold64(acc[0] + (uint64_t)v[i] * a0.x + (uint64_t)v[i + 1] * a1.x);
+                acc[1] = fold64(acc[1] + (uint64_t)v[i] * a0.y + (uint64_t)v[i + 1] * a1.y);
+                acc[2] = fold64(acc[2] + (uint64_t)v[i] * a0.z + (uint64_t)v[i + 1] * a1.z);
+                acc[3] = fold64(acc[3] + (uint64_t)v[i] * a0.w + (uint64_t)v[i + 1] * a1.w);
+            }
         }
         __syncwarp();
-        TS_UNROLL
-        for (int i = 0; i < 16; i += 2) {
-            const uint4 a0 = __ldg(apow + 16 * blk + i), a1 = __ldg(apow + 16 * blk + i + 1);
-            acc[0] = fold64(acc[0] + (uint64_t)v[i] * a0.x + (uint64_t)v[i + 1] * a1.x);
-            acc[1] = fold64(acc[1] + (uint64_t)v[i] * a0.y + (uint64_t)v[i + 1] * a1.y);
-            acc[2] = fold64(acc[2] + (uint64_t)v[i] * a0.z + (uint64_t)v[i + 1] * a1.z);
-            acc[3] = fold64(acc[3] + (uint64_t)v[i] * a0.w + (uint64_t)v[i + 1] * a1.w);
-        }
     }
 #undef TS_DOT_FETCH
     if (row0 + lane < rows) {

@@ -1656,7 +1656,7 @@ static int dot_ext_powers_launch(ts_ctx *c, const ts_matrix *m, const uint32_t *
         sg.seg_w = (uint32_t)m->width;
         sg.log_seg_w = 0;
         TS_LAUNCH(kfn, (unsigned)((m->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
-                  (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, sg, m->rows, (uint32_t)m->width,
+                  fold::DOT_SMEM_BYTES, c->stream, sg, m->rows, (uint32_t)m->width,
                   (const uint4 *)apow_dev, (uint4 *)o->d, accumulate);
         return check_launch(c, "dot_rows_fast_kernel");
     }
@@ -1739,7 +1739,7 @@ int ts_dot_ext_powers_blocks(ts_ctx *c, ts_matrix *const *blocks, size_t n_block
     auto kfn = fold::dot_rows_fast_kernel;
     const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
     TS_LAUNCH(kfn, (unsigned)((acc->rows + per_block - 1) / per_block), fold::DOT_FAST_WARPS * 32,
-              (size_t)fold::DOT_FAST_WARPS * 512 * 4, c->stream, sg, acc->rows, (uint32_t)total, (const uint4 *)alpha_powers->d,
+              fold::DOT_SMEM_BYTES, c->stream, sg, acc->rows, (uint32_t)total, (const uint4 *)alpha_powers->d,
               (uint4 *)acc->d, 0);
     return check_launch(c, "dot_rows_fast_kernel");
 }
