@@ -309,6 +309,26 @@ def run_b200(a):
                             "time (profiles/r01/README.md, 'compute-only' experiment); Blake3 leaves run the ALU pipe at 74 % and "
                             "issue on 73 % of cycles (profiles/r01/v11_ncu_full.md)"}
         lde_ms = sum(per_kind.get(k, {}).get("ms_per_step", 0) for k in ("ntt_pass", "lde_mid"))
+        # INT32 view of the LDE (the bound that actually applies): butterflies per second of this rank's
+        # shard against the butterfly issue rate measured on a B200 by profiles/tools/int_pipes.cu
+        int32 = None
+        try:
+            rate = None
+            for ln in (ROOT / "profiles" / "r01" / "int_pipes_b200_v2.jsonl").read_text().splitlines():
+                rec = json.loads(ln)
+                if rec.get("test") == "dif_butterfly":
+                    rate = rec["lane_ops_per_clk_per_sm_at_max_clock"]
+            if rate and lde_ms and clocks and clocks.get("sm_mhz"):
+                n_, w_ = 1 << a.log_rows, a.width // world
+                bf = (0.5 * a.log_rows * n_ + 0.5 * a.log_rows * (n_ << a.log_blowup)) * w_  # inverse + 2^b forward size-n
+                sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                peak_bf = rate * sms * clocks["sm_mhz"] * 1e6
+                int32 = {"butterflies_per_step": bf, "achieved_per_s": bf / (lde_ms * 1e-3), "peak_per_s": peak_bf,
+                         "frac": bf / (lde_ms * 1e-3) / peak_bf,
+                         "peak_source": "profiles/r01/int_pipes_b200_v2.jsonl dif_butterfly x SMs x sm_mhz (twiddle-only "
+                                        "multiplies of the rounds are not counted as butterflies)"}
+        except Exception:  # the extra view must never break the bench line
+            int32 = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -320,7 +340,8 @@ def run_b200(a):
             "stages": per_kind, "phases_last_step_ms": phases,
             "lde_stage": {"alg_GB": alg["lde_stage_5B_per_elem"] / 1e9, "ms": lde_ms,
                           "achieved_GBs": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) if lde_ms else None,
-                          "frac_of_hbm_peak": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) / peak if lde_ms else None},
+                          "frac_of_hbm_peak": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) / peak if lde_ms else None,
+                          "int32": int32},
             "result": {"root": last["root"].hex() if last else None, "final_poly": last["final_poly"] if last else None},
         }
         if not a.no_cpu_baseline and world == 1:

@@ -324,6 +324,7 @@ struct FastMidParams {
     FastTables t;
     const uint2 *pre_tab;   // [2^b][2^D]
     const uint2 *lane_tab;  // [2^b][2^klo_bits]
+    uint32_t n_tiles = 0;   // ntt_pm lde_mid: tiles in total; a CTA walks a contiguous range of them (0: one tile per CTA)
 };
 constexpr int MID_NT = TS_MID_NT;
 

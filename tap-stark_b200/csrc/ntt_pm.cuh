@@ -444,6 +444,46 @@ TS_D void dit_r4_ld(uint4 *tile, const uint32_t *src, size_t row_base, uint32_t 
     }
 }
 
+// ---- cp.async (LDGSTS) tile prefetch: 16 bytes straight into the position-major tile ---------------------------
+TS_D void cp_async16(uint4 *smem_dst, const uint32_t *gsrc, bool valid) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 16 : 0;  // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+#else
+    *smem_dst = valid ? *reinterpret_cast<const uint4 *>(gsrc) : make_uint4(0, 0, 0, 0);
+#endif
+}
+TS_D void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+TS_D void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+template <int D, bool BREV, int NT, int NQv = dnq(D)>
+TS_D void prefetch_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
+                        uint32_t ncols, uint32_t col0, int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int TOTAL = G::L * G::NQ;
+    TS_UNROLL
+    for (int u = 0; u < TOTAL / NT; u++) {
+        const int it = u * NT + tid;
+        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
+        const uint32_t r = BREV ? brev_bits(q, D) : q;
+        const uint32_t col = col0 + 4 * h;
+        const bool ok = col < ncols;
+        cp_async16(tile + (hx<D>(h) ^ sigma(q)), src + word_off(row_base + (size_t)r * row_stride, ok ? col : 0, pitch, slice), ok);
+    }
+    cp_async_commit();
+}
+
+
 // ---- kernels ------------------------------------------------------------------------------------------------
 #ifndef TS_PM_PASS_MINBLOCKS
 #define TS_PM_PASS_MINBLOCKS 3
@@ -524,12 +564,6 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
     uint2 *i3 = i2 + 256;
     uint4 *post = reinterpret_cast<uint4 *>(i3 + 32);    // post twiddles w_n^(Kc brev(p)), two planes (dif_r4_st)
     const int tid = threadIdx.x;
-#ifdef TS_EXP_SAMETILE
-    const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = 0;
-#else
-    const uint32_t cs = blockIdx.x % p.n_col_slices, Kc = blockIdx.x / p.n_col_slices;
-#endif
-    const uint32_t col0 = cs << (14 - D);
     const int m = D + p.klo_bits;
     const FastTables &t = p.t;
     for (int e = tid; e < R1 * 256; e += PM_MID_NT) {
@@ -547,15 +581,33 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         f3[e] = __ldg(t.tw_small + ((g * brev_bits(i, 3)) << (t.small_log - 5)));
         i3[e] = __ldg(t.tw_small_inv + ((g * i) << (t.small_log - 5)));
     }
-    // the inter-digit twiddles depend on (Kc, position) only: gathered once per CTA (2^D scattered 8-byte reads of the
+    // One CTA per SM walks a CONTIGUOUS range of tiles (tile = Kc * n_col_slices + column slice): the round tables
+    // above are filled once per CTA instead of once per tile (profiles/r01: 4 % of the stall samples sat on those fills,
+    // and with one resident CTA every tile boundary is an idle SM), and the post-twiddle table is regathered only when
+    // Kc changes, i.e. once per n_col_slices tiles.
+    const uint32_t n_tiles = p.n_tiles ? p.n_tiles : gridDim.x;
+    const uint32_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tile_begin = blockIdx.x * per_cta, tile_end = tile_begin + per_cta < n_tiles ? tile_begin + per_cta : n_tiles;
+    uint32_t post_Kc = 0xffffffffu;
+    bool prefetched = false;
+    for (uint32_t tile_id = tile_begin; tile_id < tile_end; tile_id++) {
+#ifdef TS_EXP_SAMETILE
+    const uint32_t cs = tile_id % p.n_col_slices, Kc = 0;
+#else
+    const uint32_t cs = tile_id % p.n_col_slices, Kc = tile_id / p.n_col_slices;
+#endif
+    const uint32_t col0 = cs << (14 - D);
+    __syncthreads();  // the previous tile's last round has finished with W and the post table; the tables above are visible
+    // the inter-digit twiddles depend on (Kc, position) only: gathered once per Kc (2^D scattered 8-byte reads of the
     // big table) instead of once per coset, and under the latency of the tile load that follows
-    if (p.klo_bits > 0) {
+    if (p.klo_bits > 0 && Kc != post_Kc) {
         for (int e = tid; e < G::L / 2; e += PM_MID_NT) {
             const uint32_t blk = e & (G::L / 4 - 1), c0 = 2 * (e / (G::L / 4));
             const uint2 w0 = btw<false>(t, (Kc * brev_bits(4 * blk + c0, D)) << p.tw_shift);
             const uint2 w1 = btw<false>(t, (Kc * brev_bits(4 * blk + c0 + 1, D)) << p.tw_shift);
             post[e] = make_uint4(w0.x, w0.y, w1.x, w1.y);
         }
+        post_Kc = Kc;
     }
     // inverse sub-transform on the lowest digit: rows brev(Kc)*L + x, loaded into bit-reversed positions
 #if defined(TS_PM_NO_FUSED_IO) || defined(TS_EXP_NOCOMPUTE)
@@ -566,12 +618,18 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
     for (uint32_t j = 0; j < (1u << p.b); j++)
         store_tile<D, PM_MID_NT>(A, p.dst, ((size_t)brev_bits(j, p.b) << m) + Kc, (size_t)1 << p.klo_bits, p.dst_pitch,
                                  p.dst_slice, p.ncols, col0, tid);
-    return;
+    continue;
 #endif
 #ifdef TS_PM_NO_FUSED_IO
     dit_r4<D, PM_MID_NT>(A, tid);
 #else
-    dit_r4_ld<D, PM_MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    if (prefetched) {  // this tile's rows were copied into A (cp.async) behind the previous tile's last coset
+        cp_async_wait<0>();
+        __syncthreads();
+        dit_r4<D, PM_MID_NT>(A, tid);
+    } else {
+        dit_r4_ld<D, PM_MID_NT>(A, p.src, (size_t)brev_bits(Kc, p.klo_bits) << D, p.src_pitch, p.src_slice, p.ncols, col0, tid);
+    }
 #endif
     __syncthreads();
     dit_r3<D, true, PM_MID_NT>(A, t, i3, tid);
@@ -584,6 +642,20 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
         __syncthreads();  // orders the last DIT round / the previous coset's store before W is rewritten
         dif_r1<D, false, true, true, PM_MID_NT>(A, W, t, f1, p.pre_tab + ((size_t)j << D), lw, tid);
         __syncthreads();
+#if !defined(TS_PM_NO_FUSED_IO) && defined(TS_PM_MID_PREFETCH)  // measured slower (19.6 vs 19.1 ms): opt-in build flag
+        if (j + 1 == (1u << p.b) && tile_id + 1 < tile_end) {
+            // A is dead from here on: start the next tile's (bit-reversed) row copy so that it lands during R2..R4
+            const uint32_t nt = tile_id + 1;
+#ifdef TS_EXP_SAMETILE
+            const uint32_t ncs = nt % p.n_col_slices, nKc = 0;
+#else
+            const uint32_t ncs = nt % p.n_col_slices, nKc = nt / p.n_col_slices;
+#endif
+            prefetch_tile<D, true, PM_MID_NT>(A, p.src, (size_t)brev_bits(nKc, p.klo_bits) << D, 1, p.src_pitch, p.src_slice, p.ncols,
+                                              ncs << (14 - D), tid);
+            prefetched = true;
+        }
+#endif
         dif_r2<D, false, true, PM_MID_NT>(W, t, f2, tid);
         __syncthreads();
         dif_r3<D, false, true, PM_MID_NT>(W, t, f3, tid);
@@ -603,6 +675,7 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
                                                   tid);
 #endif
     }
+    }  // tile loop
 }
 
 
@@ -616,44 +689,6 @@ __global__ void __launch_bounds__(PM_MID_NT, 1) lde_mid_pm_kernel(nttf::FastMidP
 // cp.async (LDGSTS, 16 B, straight into the position-major tile) prefetches tile i+1 while tile i is transformed,
 // and the STG.128 of tile i drain while tile i+1 is transformed.
 namespace nttp {
-
-TS_D void cp_async16(uint4 *smem_dst, const uint32_t *gsrc, bool valid) {
-#if defined(__CUDA_ARCH__)
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 16 : 0;  // src-size 0: zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-#else
-    *smem_dst = valid ? *reinterpret_cast<const uint4 *>(gsrc) : make_uint4(0, 0, 0, 0);
-#endif
-}
-TS_D void cp_async_commit() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-TS_D void cp_async_wait() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-
-template <int D, bool BREV, int NT, int NQv = dnq(D)>
-TS_D void prefetch_tile(uint4 *tile, const uint32_t *src, size_t row_base, size_t row_stride, uint32_t pitch, size_t slice,
-                        uint32_t ncols, uint32_t col0, int tid) {
-    using G = Geo<D, NQv>;
-    constexpr int TOTAL = G::L * G::NQ;
-    TS_UNROLL
-    for (int u = 0; u < TOTAL / NT; u++) {
-        const int it = u * NT + tid;
-        const uint32_t h = it & (G::NQ - 1), q = it / G::NQ;
-        const uint32_t r = BREV ? brev_bits(q, D) : q;
-        const uint32_t col = col0 + 4 * h;
-        const bool ok = col < ncols;
-        cp_async16(tile + (hx<D>(h) ^ sigma(q)), src + word_off(row_base + (size_t)r * row_stride, ok ? col : 0, pitch, slice), ok);
-    }
-    cp_async_commit();
-}
 
 #ifndef TS_PM2_NT
 #define TS_PM2_NT 512

@@ -542,15 +542,19 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
                 TS_LAUNCH(kfn, grid, nttp::PM2_NT, smem2, c->stream, pp);
             }
         } else if (use_pm()) {
+            // one CTA per SM (the kernel's 180+ KiB of shared memory allow no more), each walking a contiguous tile range
+            fp.n_tiles = (uint32_t)blocks;
+            const unsigned grid = getenv("TS_MID_NOT_PERSISTENT") ? (unsigned)blocks
+                                                                  : (unsigned)std::min<size_t>(blocks, (size_t)c->num_sms);
             if (dK == 9) {
                 auto kfn = nttp::lde_mid_pm_kernel<9>;
-                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+                TS_LAUNCH(kfn, grid, nttp::PM_MID_NT, smem, c->stream, fp);
             } else if (dK == 10) {
                 auto kfn = nttp::lde_mid_pm_kernel<10>;
-                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+                TS_LAUNCH(kfn, grid, nttp::PM_MID_NT, smem, c->stream, fp);
             } else {
                 auto kfn = nttp::lde_mid_pm_kernel<11>;
-                TS_LAUNCH(kfn, (unsigned)blocks, nttp::PM_MID_NT, smem, c->stream, fp);
+                TS_LAUNCH(kfn, grid, nttp::PM_MID_NT, smem, c->stream, fp);
             }
         } else if (dK == 9) {
             auto kfn = nttf::lde_mid_fast_kernel<9>;
