@@ -53,6 +53,9 @@ struct ts_ctx {
     // second compute stream: the leaf hash of column chunk k runs here beside the LDE of chunk k+1 (lde_hash_overlapped)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side = nullptr;
+    // set around calls whose kernels share the GPU with other work (the sharded prover's LDE runs beside the NCCL
+    // all-to-all of the previous column chunk): persistent one-CTA-per-SM launches are avoided there
+    bool shares_gpu = false;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_used[2] = {false, false};
     uint32_t *stage[2] = {nullptr, nullptr};
@@ -542,10 +545,15 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
                 TS_LAUNCH(kfn, grid, nttp::PM2_NT, smem2, c->stream, pp);
             }
         } else if (use_pm()) {
-            // one CTA per SM (the kernel's 180+ KiB of shared memory allow no more), each walking a contiguous tile range
+            // one resident CTA per SM (the kernel's 180+ KiB of shared memory allow no more), each walking a contiguous
+            // tile range (8 ranges per SM: still ~50 tiles per table fill, and the ranges rebalance if an SM is late).
+            // Not when the GPU is shared (ts_coset_lde_batch_into / _scatter, the sharded prover): beside the NCCL
+            // all-to-all of the previous column chunk the long-lived CTAs were displaced and ran late (N=2: 11.4 ->
+            // 12.3 ms with 8 ranges per SM, N=8: 3.1 -> 4.6 ms with one), so those calls launch one CTA per tile.
             fp.n_tiles = (uint32_t)blocks;
-            const unsigned grid = getenv("TS_MID_NOT_PERSISTENT") ? (unsigned)blocks
-                                                                  : (unsigned)std::min<size_t>(blocks, (size_t)c->num_sms);
+            const unsigned grid = (c->shares_gpu || getenv("TS_MID_NOT_PERSISTENT"))
+                                      ? (unsigned)blocks
+                                      : (unsigned)std::min<size_t>(blocks, (size_t)c->num_sms * 8);
             if (dK == 9) {
                 auto kfn = nttp::lde_mid_pm_kernel<9>;
                 TS_LAUNCH(kfn, grid, nttp::PM_MID_NT, smem, c->stream, fp);
@@ -1957,7 +1965,10 @@ int ts_coset_lde_batch_into(ts_ctx *c, const ts_matrix *evals, unsigned added_bi
                             ts_matrix *out) {
     if (out->rows != (evals->rows << added_bits) || out->width != evals->width)
         TS_FAIL(c, TS_ERR_ARG, "coset_lde_batch_into: out must be (rows<<added_bits) x width");
-    return lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, out->d);
+    c->shares_gpu = true;
+    const int rc = lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, out->d);
+    c->shares_gpu = false;
+    return rc;
 }
 int ts_coset_lde_batch_scatter(ts_ctx *c, const ts_matrix *evals, unsigned added_bits, uint32_t shift_monty,
                                uint32_t *const *owner_ptrs, size_t n_owners, size_t dst_pitch) {
@@ -1966,7 +1977,10 @@ int ts_coset_lde_batch_scatter(ts_ctx *c, const ts_matrix *evals, unsigned added
     PeerDst pd;
     pd.n = (int)n_owners;
     for (size_t i = 0; i < 8; i++) pd.ptr[i] = i < n_owners ? owner_ptrs[i] : nullptr;
-    return lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, nullptr, 0, dst_pitch, &pd);
+    c->shares_gpu = true;
+    const int rc = lde_committed(c, evals->d, evals->rows, evals->width, added_bits, shift_monty, nullptr, 0, dst_pitch, &pd);
+    c->shares_gpu = false;
+    return rc;
 }
 // CUDA IPC plumbing for the peer-mapped receive buffers (one process per GPU)
 int ts_device_malloc(ts_ctx *c, size_t bytes, void **out) {
