@@ -57,6 +57,21 @@ pub mod sys {
         pub fn ts_challenger_sample_ext(c: *mut ts_challenger, out: *mut u32);
         pub fn ts_fri_fold_ext_host(ctx: *mut ts_ctx, input: *const u32, h: usize, beta_monty: *const u32,
                                     out: *mut u32) -> c_int;
+        // Pcs::open on the device-resident LDE (fri/src/two_adic_pcs.rs:260-419)
+        pub fn ts_inv_denoms(ctx: *mut ts_ctx, log_h: c_uint, z_monty: *const u32, out: *mut *mut ts_matrix) -> c_int;
+        pub fn ts_interpolate_low_coset(ctx: *mut ts_ctx, lde: *const ts_matrix, n: usize, z_monty: *const u32,
+                                        inv_denoms: *const ts_matrix, ys_out: *mut u32) -> c_int;
+        pub fn ts_reduce_opening_acc(ctx: *mut ts_ctx, dot: *const ts_matrix, inv_denoms: *const ts_matrix,
+                                     alpha_pow_offset_monty: *const u32, reduced_ys_monty: *const u32,
+                                     acc: *mut ts_matrix) -> c_int;
+        pub fn ts_challenger_grind(c: *mut ts_challenger, bits: c_uint, ext: c_int, witness: *mut u32) -> c_int;
+        // quotient_values of uni_stark::prove (uni-stark/src/prover.rs:122-194) and the device-to-device second commit
+        pub fn ts_quotient_values(ctx: *mut ts_ctx, trace_lde: *const ts_matrix, log_n: c_uint,
+                                  log_quotient_degree: c_uint, program: *const u32, n_instr: usize,
+                                  consts_monty: *const u32, n_consts: usize, public_values_monty: *const u32,
+                                  n_public: usize, alpha_monty: *const u32, chunks_out: *mut *mut ts_matrix) -> c_int;
+        pub fn ts_pcs_commit(ctx: *mut ts_ctx, evals: *const *mut ts_matrix, domain_shifts_monty: *const u32, n: usize,
+                             log_blowup: c_uint, layout: c_int, root: *mut u8, out: *mut *mut ts_tree) -> c_int;
     }
 }
 

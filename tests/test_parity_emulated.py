@@ -209,3 +209,26 @@ def test_stark_program_errors(ts, ctx):
         rc = ctx._L.ts_quotient_values(ctx._h, m._h, 3, 0, p.ctypes.data_as(C.c_void_p), 1, one.ctypes.data_as(C.c_void_p), 0,
                                        one.ctypes.data_as(C.c_void_p), 0, alpha.ctypes.data_as(C.c_void_p), out)
         assert rc == 2  # TS_ERR_ARG
+
+
+@pytest.mark.parametrize("widths", [[8, 8, 8], [8, 4], [12]])
+def test_dot_ext_powers_blocks(ts, ctx, orc, widths):
+    """ts_dot_ext_powers_blocks: a row held as several column blocks (equal power-of-two widths: one pass over all of
+    them; ragged: one accumulating pass per block) against the oracle's dot over the concatenated matrix."""
+    import ctypes as C
+
+    import numpy as np
+
+    rows = 96
+    mats = [pc.rand_mat(50 + i, rows, w) for i, w in enumerate(widths)]
+    alpha = np.array([5, 6, 7, 8], dtype=np.uint32)
+    dev = [ts.DeviceMatrix.from_canonical(ctx, m) for m in mats]
+    ap = C.c_void_p()
+    am = ts.to_monty(alpha)
+    ctx.check(ctx._L.ts_alpha_powers(ctx._h, am.ctypes.data_as(C.c_void_p), sum(widths), C.byref(ap)), "alpha_powers")
+    acc = ts.DeviceMatrix.from_canonical(ctx, np.zeros((rows, 4), dtype=np.uint32))
+    arr = (C.c_void_p * len(dev))(*[d._h for d in dev])
+    ctx.check(ctx._L.ts_dot_ext_powers_blocks(ctx._h, arr, len(dev), ap, acc._h), "dot_ext_powers_blocks")
+    ctx._L.ts_matrix_free(ap)
+    ref = orc.dot_ext_powers(np.ascontiguousarray(np.concatenate(mats, axis=1)), alpha)
+    assert np.array_equal(acc.to_canonical(), ref)
