@@ -232,3 +232,21 @@ def test_dot_ext_powers_blocks(ts, ctx, orc, widths):
     ctx._L.ts_matrix_free(ap)
     ref = orc.dot_ext_powers(np.ascontiguousarray(np.concatenate(mats, axis=1)), alpha)
     assert np.array_equal(acc.to_canonical(), ref)
+
+
+def test_stark_edge_sizes(ts, ctx, orc):
+    """Smallest traces (2 and 4 rows) still prove and verify; a quotient domain larger than the committed LDE
+    (log_quotient_degree > log_blowup) is an argument error, as get_evaluations_on_domain would refuse it."""
+    import importlib
+
+    import airs
+
+    for n in (2, 4):
+        trace = airs.fibonacci_trace(3, 5, n)
+        pc.check_stark_prove_verify(ts, ctx, orc, airs.FibonacciAir(), trace, [3, 5, int(trace[-1, 1])], 2, tamper=False)
+    st = importlib.import_module(ts.__name__ + ".stark")
+    air = airs.MulAir(degree=5, reps=1)  # quotient degree 4
+    mmcs = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(1, 2, 4, mmcs))
+    with pytest.raises(ts.TapStarkError):
+        st.prove(pcs, air, ts.BfChallenger(), airs.mul_trace(air, 16, 3), [])
