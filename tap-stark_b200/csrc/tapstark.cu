@@ -155,7 +155,11 @@ void pool_trim(ts_ctx *c) {
     c->pool_free.clear();
 }
 cudaError_t pool_alloc(ts_ctx *c, void **p, size_t bytes) {
+#ifdef TS_EMULATE  // exact sizes: under the AddressSanitizer build of the emulator every byte past the end is a red zone
+    const size_t sz = std::max<size_t>(bytes, 1);
+#else
     const size_t sz = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+#endif
     auto it = c->pool_free.find(sz);
     if (it != c->pool_free.end()) {
         *p = it->second;
