@@ -250,3 +250,11 @@ def test_stark_edge_sizes(ts, ctx, orc):
     pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(1, 2, 4, mmcs))
     with pytest.raises(ts.TapStarkError):
         st.prove(pcs, air, ts.BfChallenger(), airs.mul_trace(air, 16, 3), [])
+
+
+def test_stark_wide_air(ts, ctx, orc):
+    """A C4-shaped AIR (66 triples = 198 columns, not a multiple of 4; ~400-instruction constraint program)."""
+    import airs
+
+    air = airs.MulAir(degree=3, reps=66)
+    pc.check_stark_prove_verify(ts, ctx, orc, air, airs.mul_trace(air, 1 << 4, 9), [], 2, num_queries=2, tamper=False)
