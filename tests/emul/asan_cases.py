@@ -20,7 +20,7 @@ def main(lib):
     ts.load_library(lib, allow_emulated=True)
     ctx = ts.Context(0)
     pc.check_lde(ts, ctx, orc, 12, 3, 1)            # generic digit kernels, odd width
-    pc.check_lde(ts, ctx, orc, 18, 12, 2)           # position-major passes + persistent lde_mid, ragged column slice
+    pc.check_lde(ts, ctx, orc, 18, 12, 1)           # position-major passes + persistent lde_mid, ragged column slice
     pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)  # ragged rows / columns of the warp-transposing kernels
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
     pc.check_mmcs(ts, ctx, orc, [(64, 5), (64, 3), (16, 9)], 0)
