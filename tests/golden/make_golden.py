@@ -130,6 +130,41 @@ def main():
     g["commit_phase"] = {"log_n": log_n, "log_blowup": b, "evals": rows, "commits": commits, "betas": betas,
                          "final_poly": folded[0]}
 
+    # --- row f3: quotient values of the reference's Fibonacci AIR (uni-stark/tests/fib_air.rs: 2^3 rows, log_blowup 2)
+    # by definition (uni-stark/src/prover.rs:122-194; selectors [MEM] p3-commit selectors_on_coset), big ints only
+    log_n, b = 3, 2
+    n = 1 << log_n
+    tr = [[0, 1]]
+    for _ in range(1, n):
+        tr.append([tr[-1][1], (tr[-1][0] + tr[-1][1]) % P])
+    pis = [0, 1, tr[-1][1]]
+    lde = pyref.lde_committed_def(tr, b, 31)
+    root, _ = pyref.merkle_root_single(H, lde)
+    chal = pyref.PyChallenger(H)
+    chal.observe_digest(root)
+    alpha = chal.sample_ef()
+    tq = [lde[pyref.bitrev(i, log_n)] for i in range(n)]  # first n committed rows, re-bit-reversed: the trace on g*H_n
+    w_n = pyref.two_adic_generator(log_n)
+    w_n_inv = pow(w_n, P - 2, P)
+    quotient = []
+    for i in range(n):
+        x = 31 * pow(w_n, i, P) % P
+        zh = (pow(x, n, P) - 1) % P
+        first = zh * pow((x - 1) % P, P - 2, P) % P
+        last = zh * pow((x - w_n_inv) % P, P - 2, P) % P
+        trans = (x - w_n_inv) % P
+        l, nx = tq[i], tq[(i + 1) % n]
+        cons = [first * (l[0] - pis[0]), first * (l[1] - pis[1]), trans * (l[1] - nx[0]), trans * (l[0] + l[1] - nx[1]),
+                last * (l[1] - pis[2])]
+        acc = [0, 0, 0, 0]
+        for c in cons:  # accumulator = accumulator * alpha + constraint (uni-stark/src/folder.rs:60-64)
+            acc = pyref.ef_mul(acc, alpha)
+            acc[0] = (acc[0] + c) % P
+        quotient.append(pyref.ef_scale(acc, pow(zh, P - 2, P)))
+    g["stark_fibonacci"] = {"src": "uni-stark/tests/fib_air.rs:117-149, uni-stark/src/prover.rs:122-194", "log_n": log_n,
+                            "log_blowup": b, "trace": tr, "public_values": pis, "trace_root": root.hex(), "alpha": alpha,
+                            "quotient": quotient}
+
     out = Path(__file__).with_name("golden.json")
     out.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {out} ({out.stat().st_size} bytes)")

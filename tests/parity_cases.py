@@ -312,3 +312,19 @@ def check_stark_prove_verify(ts, ctx, orc, air, trace, public_values, log_blowup
         raise AssertionError("tampered opened value accepted")
     v[0][0] = (int(v[0][0]) - 1) % P
     return proof
+
+
+def check_stark_golden(ts, ctx, g):
+    """Device quotient values of the Fibonacci AIR against the golden fixture (big-int definition)."""
+    from importlib import import_module
+
+    import airs
+
+    st = import_module(ts.__name__ + ".stark")
+    mmcs = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mmcs, ts.FriConfig(g["log_blowup"], 2, 4, mmcs))
+    trace = np.array(g["trace"], dtype=np.uint32)
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(trace.shape[0]), ts.DeviceMatrix.from_canonical(ctx, trace))])
+    assert root.hex() == g["trace_root"]
+    chunks = st.quotient_values(pcs, data, airs.FibonacciAir(), g["public_values"], g["log_n"], 0, g["alpha"])
+    assert len(chunks) == 1 and chunks[0].to_canonical().tolist() == g["quotient"]

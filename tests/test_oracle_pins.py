@@ -216,3 +216,23 @@ def test_commit_phase_mixed_inputs_verify(orc):
             folded = orc.fold_row_ef(pair, lfh, res["betas"][r], layer[2 * pair], layer[2 * pair + 1])
             idx = pair
         assert np.array_equal(folded, res["final_poly"])
+
+
+def test_stark_fibonacci_quotient_golden(golden, orc):
+    """Row f3: the oracle's folder-based quotient values equal the big-int definition frozen in golden.json
+    (uni-stark/src/prover.rs:122-194 on the reference's Fibonacci AIR)."""
+    import numpy as np
+
+    import airs
+    from oracle import stark as OS
+
+    g = golden["stark_fibonacci"]
+    trace = np.array(g["trace"], dtype=np.uint32)
+    assert np.array_equal(trace, airs.fibonacci_trace(0, 1, 1 << g["log_n"]))
+    lde = orc.pcs_lde_committed(trace, g["log_blowup"])
+    assert orc.mmcs_commit([lde]).root.hex() == g["trace_root"]
+    ch = orc.BfChallenger()
+    ch.observe_digest(bytes.fromhex(g["trace_root"]))
+    assert [int(x) for x in ch.sample_ef()] == g["alpha"]
+    chunks = OS.quotient_values(airs.FibonacciAir(), g["public_values"], lde, g["log_n"], 0, g["alpha"])
+    assert len(chunks) == 1 and chunks[0].tolist() == g["quotient"]

@@ -258,3 +258,7 @@ def test_stark_wide_air(ts, ctx, orc):
 
     air = airs.MulAir(degree=3, reps=66)
     pc.check_stark_prove_verify(ts, ctx, orc, air, airs.mul_trace(air, 1 << 4, 9), [], 2, num_queries=2, tamper=False)
+
+
+def test_stark_quotient_golden(ts, ctx, golden):
+    pc.check_stark_golden(ts, ctx, golden["stark_fibonacci"])

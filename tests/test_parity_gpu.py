@@ -354,3 +354,7 @@ def test_stark_program_errors(ts, ctx):
         rc = ctx._L.ts_quotient_values(ctx._h, m._h, 3, 0, p.ctypes.data_as(C.c_void_p), 1, one.ctypes.data_as(C.c_void_p), 0,
                                        one.ctypes.data_as(C.c_void_p), 0, alpha.ctypes.data_as(C.c_void_p), out)
         assert rc == 2  # TS_ERR_ARG
+
+
+def test_stark_quotient_golden(ts, ctx, golden):
+    pc.check_stark_golden(ts, ctx, golden["stark_fibonacci"])
