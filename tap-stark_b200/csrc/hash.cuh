@@ -383,6 +383,41 @@ __global__ void __launch_bounds__(TREE_T) tree_reduce_kernel(const uint32_t *chi
     }
 }
 
+// Big layers: one thread reduces 8 consecutive children to 4 + 2 + 1 parents held in registers -- three levels per
+// launch, no barrier, every lane busy (tree_reduce_kernel halves its active threads per level and waits at a barrier
+// between levels: profiles/r01, 6 of 10 stall cycles).  n_children must be a multiple of 8.
+__global__ void __launch_bounds__(128) tree_reduce3_kernel(const uint32_t *__restrict__ children, size_t n_children,
+                                                           uint32_t *__restrict__ out0, uint32_t *__restrict__ out1,
+                                                           uint32_t *__restrict__ out2) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_children / 8) return;
+    const uint4 *in = reinterpret_cast<const uint4 *>(children) + t * 16;  // 8 digests = 16 uint4
+    uint32_t p[4][8];
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) {
+        const uint4 a0 = in[4 * k], a1 = in[4 * k + 1], b0 = in[4 * k + 2], b1 = in[4 * k + 3];
+        const uint32_t l[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t r[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        compress_pair(l, r, CHUNK_START | CHUNK_END | ROOT, p[k]);
+        uint4 *o = reinterpret_cast<uint4 *>(out0) + (4 * t + k) * 2;
+        o[0] = make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
+        o[1] = make_uint4(p[k][4], p[k][5], p[k][6], p[k][7]);
+    }
+    uint32_t q[2][8];
+    TS_UNROLL
+    for (int j = 0; j < 2; j++) {
+        compress_pair(p[2 * j], p[2 * j + 1], CHUNK_START | CHUNK_END | ROOT, q[j]);
+        uint4 *o = reinterpret_cast<uint4 *>(out1) + (2 * t + j) * 2;
+        o[0] = make_uint4(q[j][0], q[j][1], q[j][2], q[j][3]);
+        o[1] = make_uint4(q[j][4], q[j][5], q[j][6], q[j][7]);
+    }
+    uint32_t r8[8];
+    compress_pair(q[0], q[1], CHUNK_START | CHUNK_END | ROOT, r8);
+    uint4 *o = reinterpret_cast<uint4 *>(out2) + t * 2;
+    o[0] = make_uint4(r8[0], r8[1], r8[2], r8[3]);
+    o[1] = make_uint4(r8[4], r8[5], r8[6], r8[7]);
+}
+
 // P3 injection layer: out[i] = H( H(prev[2i] || prev[2i+1]) || rows_digest[i] )
 __global__ void compress_inject_kernel(const uint32_t *children, const uint32_t *rows_digest, size_t n_par,
                                        uint32_t *out) {

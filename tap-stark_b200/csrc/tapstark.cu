@@ -894,6 +894,17 @@ int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
                 break;
             levels++;
         }
+        const size_t n_ch = t->hmax >> (l - 1);
+        if (levels >= 3 && n_ch >= ((size_t)1 << 14) && getenv("TS_NO_TREE3") == nullptr) {
+            // big layer: three levels per launch, one thread per 8 children
+            KScope ks(c, TS_K_TREE);
+            auto kfn3 = b3::tree_reduce3_kernel;
+            TS_LAUNCH(kfn3, (unsigned)((n_ch / 8 + 127) / 128), 128, 0, c->stream, children, n_ch,
+                      t->digests + t->layer_off[l] * 8, t->digests + t->layer_off[l + 1] * 8, t->digests + t->layer_off[l + 2] * 8);
+            TS_TRY(check_launch(c, "tree_reduce3_kernel"));
+            l += 3;
+            continue;
+        }
         b3::TreeLevels lv;
         lv.levels = levels;
         for (int i = 0; i < b3::TREE_MAX_LEVELS; i++)

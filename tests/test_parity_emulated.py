@@ -262,3 +262,10 @@ def test_stark_wide_air(ts, ctx, orc):
 
 def test_stark_quotient_golden(ts, ctx, golden):
     pc.check_stark_golden(ts, ctx, golden["stark_fibonacci"])
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_mmcs_big_layers(ts, ctx, orc, layout):
+    """Layers of >= 2^14 children go through tree_reduce3_kernel (one thread per 8 children, three levels per launch),
+    here followed by an injection layer (2^12 rows) and the shared-memory kernel for the top."""
+    pc.check_mmcs(ts, ctx, orc, [(1 << 16, 3), (1 << 12, 5)], layout, indices=(0, 4097, (1 << 16) - 1))
