@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "fold.cuh"
+#include "fri_tail.cuh"
 #include "hash.cuh"
 #include "host_side.h"
 #include "ntt.cuh"
@@ -56,6 +57,7 @@ struct ts_ctx {
     // set around calls whose kernels share the GPU with other work (the sharded prover's LDE runs beside the NCCL
     // all-to-all of the previous column chunk): persistent one-CTA-per-SM launches are avoided there
     bool shares_gpu = false;
+    std::vector<uint32_t> tail_final;  // final FRI layer of the last fri_tail call (Montgomery), host side
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     bool ev_free_used[2] = {false, false};
     uint32_t *stage[2] = {nullptr, nullptr};
@@ -1494,6 +1496,105 @@ int ts_fri_fold_ext_host(ts_ctx *c, const uint32_t *in_host, size_t h, const uin
 }
 
 // ---------------------------------------------------------------- commit phase (fri/src/prover.rs:93-141)
+// The remaining commit-phase rounds of a small layer in one launch (fri_tail.cuh).  `cur` (len x 4 words) is the current
+// layer; when it is owned it becomes the leaf matrix of the first tail tree (or is released), otherwise it is only read.
+// Appends to commits / trees from index `round` on and advances it; the final layer lands in c->tail_final.
+static int fri_tail(ts_ctx *c, ts_challenger *chal, uint32_t *cur, bool cur_owned, size_t len, unsigned log_blowup,
+                    uint8_t *commits, ts_tree **trees, size_t &round) {
+    const int log_len = log2_strict(len);
+    const int rounds = log_len - (int)log_blowup;
+    ftail::Params p;
+    p.layer0 = cur;
+    p.log_len0 = log_len;
+    p.rounds = rounds;
+    memcpy(p.prev_h, &chal->state[8][0], 32);
+    for (int b = 0; b < ftail::MAX_LOG_LEN + 2; b++) p.inv_gen[b] = h_to_monty(bb::cinv(bb::two_adic_generator(b)));
+    std::vector<ts_tree *> tt((size_t)rounds, nullptr);
+    uint32_t *roots_dev = nullptr;
+    int rc = TS_OK;
+    cudaError_t e = pool_alloc(c, (void **)&roots_dev, (size_t)rounds * 32);
+    if (e != cudaSuccess) rc = TS_ERR_CUDA;
+    uint32_t *layer_in = cur;
+    bool layer_owned = cur_owned;
+    for (int r = 0; r < rounds && rc == TS_OK; r++) {
+        const size_t h = len >> (r + 1);
+        ts_tree *t = new ts_tree;
+        t->ctx = c;
+        t->mats.push_back(new ts_matrix{c, layer_in, h, 8, layer_owned});  // leaves of round r (prover.rs:112)
+        t->own_mats = true;
+        t->layout = TS_LAYOUT_P3_INJECT;
+        t->order.assign(1, 0);
+        t->hmax = h;
+        t->lmax = (unsigned)log2_strict(h);
+        t->digests = nullptr;
+        size_t off = 0;
+        for (unsigned l = 0; l <= t->lmax; l++) {
+            t->layer_off.push_back(off);
+            off += h >> l;
+        }
+        tt[(size_t)r] = t;
+        uint32_t *next = nullptr;
+        if (pool_alloc(c, (void **)&t->digests, off * 32) != cudaSuccess || pool_alloc(c, (void **)&next, h * 16) != cudaSuccess) {
+            if (next) pool_release(c, next);
+            rc = TS_ERR_CUDA;
+            layer_in = nullptr;
+            break;
+        }
+        p.digests[r] = t->digests;
+        p.layers[r] = next;
+        layer_in = next;  // leaves of the next round, owned by that round's tree
+        layer_owned = true;
+    }
+    p.roots_out = roots_dev;
+    std::vector<uint32_t> host((size_t)rounds * 8 + ((size_t)4 << log_blowup));
+    if (rc == TS_OK) {
+        {
+            KScope ks(c, TS_K_FOLD);
+            auto kfn = ftail::fri_tail_kernel;
+            TS_LAUNCH(kfn, 1, ftail::NT, 12 * sizeof(uint32_t), c->stream, p);
+            rc = check_launch(c, "fri_tail_kernel");
+        }
+        if (rc == TS_OK) {
+            e = cudaMemcpyAsync(host.data(), roots_dev, (size_t)rounds * 32, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(host.data() + (size_t)rounds * 8, layer_in, (size_t)16 << log_blowup, cudaMemcpyDeviceToHost,
+                                    c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) {
+                c->err = std::string("fri tail read-back: ") + cudaGetErrorString(e);
+                rc = TS_ERR_CUDA;
+            }
+        }
+    } else {
+        c->err = "fri tail: allocation failed";
+    }
+    if (layer_in) pool_release(c, layer_in);  // the final layer is owned by no tree
+    if (roots_dev) pool_release(c, roots_dev);
+    if (rc == TS_OK) {
+        for (int r = 0; r < rounds; r++) {  // replay the sponge on the host: it stays the source of truth
+            const uint8_t *root = reinterpret_cast<const uint8_t *>(host.data() + (size_t)r * 8);
+            memcpy(commits + 32 * round, root, 32);
+            ts_challenger_observe_digest(chal, root);
+            uint32_t beta[4];
+            ts_challenger_sample_ext(chal, beta);
+            if (trees) trees[round] = tt[(size_t)r];
+            else ts_tree_free(tt[(size_t)r]);
+            tt[(size_t)r] = nullptr;
+            round++;
+        }
+        c->tail_final.assign(host.begin() + (size_t)rounds * 8, host.end());
+    }
+    if (cur_owned && tt[0] == nullptr && (rc != TS_OK) && cur) {
+        // failed before the first tail tree took the layer over
+        bool taken = false;
+        for (ts_tree *t : tt) taken = taken || t != nullptr;
+        if (!taken) pool_release(c, cur);
+    }
+    for (ts_tree *t : tt)
+        if (t) ts_tree_free(t);
+    return rc;
+}
+
 int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, unsigned log_blowup, ts_challenger *chal,
                         uint8_t *commits, ts_tree **trees, uint32_t final_poly[4], size_t *rounds_out) {
     if (n_inputs == 0) TS_FAIL(c, TS_ERR_ARG, "commit phase: no inputs");
@@ -1522,6 +1623,25 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         cur_owned = true;
     }
     while (len > blowup) {
+        if (len <= ((size_t)1 << ftail::MAX_LOG_LEN) && next_in >= n_inputs && chal->in_buf.empty() &&
+            getenv("TS_NO_FRI_TAIL") == nullptr) {
+            // every remaining round in one launch, sponge included (fri_tail.cuh)
+            rc = fri_tail(c, chal, cur, cur_owned, len, log_blowup, commits, trees, round);
+            cur = nullptr;  // consumed: owned by the first tail tree or released
+            cur_owned = false;
+            if (rc == TS_OK) {
+                // the tail left the final layer in c->tail_final (host)
+                len = blowup;
+                for (int i = 0; i < 4; i++) final_poly[i] = h_from_monty(c->tail_final[i]);
+                for (size_t i = 1; i < blowup; i++)
+                    if (memcmp(&c->tail_final[4 * i], &c->tail_final[0], 16) != 0) {  // prover.rs:130-134
+                        c->err = "commit phase: final layer is not constant (input not low-degree)";
+                        rc = TS_ERR_NOT_CONSTANT;
+                    }
+            }
+            if (rounds_out) *rounds_out = round;
+            return rc;
+        }
         const size_t h = len / 2;
         // leaves = RowMajorMatrix::new(folded.clone(), 2): h rows of 2 EF = 8 u32 (prover.rs:112)
         ts_matrix *leaves = new ts_matrix{c, cur, h, 8, cur_owned};
