@@ -1584,12 +1584,9 @@ static int fri_tail(ts_ctx *c, ts_challenger *chal, uint32_t *cur, bool cur_owne
         }
         c->tail_final.assign(host.begin() + (size_t)rounds * 8, host.end());
     }
-    if (cur_owned && tt[0] == nullptr && (rc != TS_OK) && cur) {
-        // failed before the first tail tree took the layer over
-        bool taken = false;
-        for (ts_tree *t : tt) taken = taken || t != nullptr;
-        if (!taken) pool_release(c, cur);
-    }
+    // error paths: trees that were set up free their layers; if not even the first one exists, the caller's owned layer
+    // has no owner yet
+    if (rc != TS_OK && cur_owned && tt[0] == nullptr) pool_release(c, cur);
     for (ts_tree *t : tt)
         if (t) ts_tree_free(t);
     return rc;
