@@ -67,3 +67,30 @@ def mul_trace(air: MulAir, n: int, seed: int) -> np.ndarray:
             t[i, 3 * r], t[i, 3 * r + 1] = a, b
             t[i, 3 * r + 2] = pow(a, air.degree - 1, P) * b % P
     return t
+
+
+class CounterAir:
+    """Exercises the rest of the AirBuilder surface: constants, negation, assert_one, when(<expression>).
+    Columns (i, flag, sq, neg): i counts 0,1,2,...; flag = 1 on every row; sq = i*i; neg = -i.  Constraints:
+    flag == 1; when(flag): sq - i*i == 0; neg + i == 0 written as -(i) - neg == 0; first row i == 0;
+    transition i' == i + 1; last row i == public[0]."""
+
+    def width(self):
+        return 4
+
+    def eval(self, builder):
+        local, nxt = builder.main()
+        i, flag, sq, neg = local
+        builder.assert_one(flag)
+        builder.when(flag).assert_zero(sq - i * i)
+        builder.assert_zero(-i - neg)
+        builder.when_first_row().assert_zero(i)
+        builder.when_transition().assert_eq(nxt[0], i + 1)
+        builder.when_last_row().assert_eq(i, builder.public_values()[0])
+
+
+def counter_trace(n: int) -> np.ndarray:
+    t = np.zeros((n, 4), dtype=np.uint32)
+    for i in range(n):
+        t[i] = (i, 1, i * i % P, (P - i) % P)
+    return t

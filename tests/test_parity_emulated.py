@@ -269,3 +269,12 @@ def test_mmcs_big_layers(ts, ctx, orc, layout):
     """Layers of >= 2^14 children go through tree_reduce3_kernel (one thread per 8 children, three levels per launch),
     here followed by an injection layer (2^12 rows) and the shared-memory kernel for the top."""
     pc.check_mmcs(ts, ctx, orc, [(1 << 16, 3), (1 << 12, 5)], layout, indices=(0, 4097, (1 << 16) - 1))
+
+
+def test_stark_counter_air(ts, ctx, orc):
+    """Constants, negation, assert_one and when(<expression>) through the symbolic builder, the program compiler and the
+    kernel's NEG / CONST operands (constraint degree 3 -> two quotient chunks)."""
+    import airs
+
+    n = 1 << 5
+    pc.check_stark_prove_verify(ts, ctx, orc, airs.CounterAir(), airs.counter_trace(n), [n - 1], 2)

@@ -358,3 +358,11 @@ def test_stark_program_errors(ts, ctx):
 
 def test_stark_quotient_golden(ts, ctx, golden):
     pc.check_stark_golden(ts, ctx, golden["stark_fibonacci"])
+
+
+def test_stark_counter_air(ts, ctx, orc):
+    """Constants, negation, assert_one, when(<expression>): the NEG / CONST operands of the constraint-program kernel."""
+    import airs
+
+    n = 1 << 8
+    pc.check_stark_prove_verify(ts, ctx, orc, airs.CounterAir(), airs.counter_trace(n), [n - 1], 2)
