@@ -42,6 +42,11 @@ def parse_args():
     ap.add_argument("--width", type=int, default=256)
     ap.add_argument("--log-blowup", type=int, default=2)
     ap.add_argument("--cpu-log-rows", type=int, default=18, help="rows of the bounded CPU sample")
+    ap.add_argument("--cpu-same-config", action="store_true",
+                    help="reference arm: additionally time ONE step of the full --log-rows configuration (about 30 s of CPU work)")
+    ap.add_argument("--seed", type=int, default=0, help="SplitMix seed of the synthetic trace (SURVEY 8d)")
+    ap.add_argument("--no-self-check", action="store_true",
+                    help="skip the in-process comparison of root / final_poly with the CPU oracle on the 2^cpu-log-rows sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -66,26 +71,30 @@ def cpu_pipeline(orc, trace, b):
     return tree.root, res
 
 
-def cpu_sample(a, steps, warmup):
+def cpu_sample(a, steps, warmup, log_rows=None):
     from oracle import oracle as orc
 
-    rows, w, b = 1 << a.cpu_log_rows, a.width, a.log_blowup
-    trace = orc.splitmix_matrix(0, rows, w)
+    cores = orc.use_all_cores()  # torch.distributed.run exports OMP_NUM_THREADS=1: set the team explicitly
+    log_rows = a.cpu_log_rows if log_rows is None else log_rows
+    rows, w, b = 1 << log_rows, a.width, a.log_blowup
+    trace = orc.splitmix_matrix(a.seed, rows, w)
     for _ in range(warmup):
         cpu_pipeline(orc, trace, b)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pipeline(orc, trace, b)
+        root, res = cpu_pipeline(orc, trace, b)
     dt = (time.perf_counter() - t0) / steps
     elems = (rows << b) * w
     return {
         "value": elems / dt,
         "unit": UNIT,
-        "cores": orc.num_threads(),
+        "cores": cores,
         "kind": "port",
-        "sample": f"oracle C port (OpenMP) of the same step on a 2^{a.cpu_log_rows}x{w} trace, log_blowup {b} "
-                  f"({elems} output elems, {dt:.2f} s/step); the reference itself is Rust and cannot be built here",
+        "sample": f"oracle C port (OpenMP, {cores} threads) of the same step on a 2^{log_rows}x{w} SplitMix trace (seed {a.seed}), "
+                  f"log_blowup {b} ({elems} output elems, {dt:.2f} s/step); the reference itself is Rust and cannot be built here",
         "ms_per_step": dt * 1e3,
+        "root": root.hex(),
+        "final_poly": [int(x) for x in res["final_poly"]],
     }
 
 
@@ -104,6 +113,11 @@ def run_reference(a):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if a.cpu_same_config and a.cpu_log_rows != a.log_rows:
+        full = cpu_sample(a, 1, 0, log_rows=a.log_rows)
+        line["same_config"] = {"value": full["value"], "unit": UNIT, "ms_per_step": full["ms_per_step"], "steps": 1,
+                               "cores": full["cores"], "root": full["root"], "final_poly": full["final_poly"],
+                               "note": "ONE untimed-warm-up-free step of the full configuration; `value` above is the K-step sample"}
     print(json.dumps(line), flush=True)
 
 
@@ -155,7 +169,8 @@ def algorithmic_bytes(n, w, b, digits):
     D = digits
     fri_rounds = max((N.bit_length() - 1) - b, 0)
     out = {
-        "ntt_pass": (D - 1) * 2 * n * w * 4 + (D - 1) * 2 * N * w * 4,
+        # two-digit LDE = P1, P2 (n rows each), P4 (N rows) as passes and P3 as "lde_mid" (ntt_v4.cuh)
+        "ntt_pass": (2 * 2 * n * w * 4 + 2 * N * w * 4) if D == 2 else ((D - 1) * 2 * n * w * 4 + (D - 1) * 2 * N * w * 4),
         "lde_mid": (n + N) * w * 4,
         "hash_leaves": N * w * 4 + N * 32 + sum((N >> (r + 1)) * 64 for r in range(fri_rounds)),
         "tree": 96 * (N - 1) + sum(96 * ((N >> (r + 1)) - 1) for r in range(fri_rounds)),
@@ -214,9 +229,33 @@ def run_b200(a):
     if world > 1:
         from tapstark_b200 import parallel as par  # column-sharded LDE / all-to-all / row-sharded hash + fold
 
-        runner = par.ShardedRunner(ts, ctx, a.log_rows, a.width, a.log_blowup, rank, world)
+        def make_runner(log_rows):
+            return par.ShardedRunner(ts, ctx, log_rows, a.width, a.log_blowup, rank, world, seed=a.seed)
     else:
-        runner = SingleGpuRunner(ts, ctx, a.log_rows, a.width, a.log_blowup)
+        def make_runner(log_rows):
+            return SingleGpuRunner(ts, ctx, log_rows, a.width, a.log_blowup, seed=a.seed)
+
+    # ---- self-check: the same pipeline on the bounded 2^cpu_log_rows sample of the same trace generator, against the
+    # CPU oracle, in this process (at N > 1 the sharded path is what is checked; only rank 0 runs the oracle)
+    self_check = None
+    if not a.no_self_check:
+        small = make_runner(a.cpu_log_rows)
+        got = small.step_resident()
+        small.close()
+        if rank == 0:
+            from oracle import oracle as orc
+
+            orc.use_all_cores()
+            ref_root, ref = cpu_pipeline(orc, orc.splitmix_matrix(a.seed, 1 << a.cpu_log_rows, a.width), a.log_blowup)
+            self_check = {
+                "sample": f"2^{a.cpu_log_rows}x{a.width}, seed {a.seed}, {world} GPU(s) vs oracle",
+                "root_match": got["root"] == ref_root,
+                "final_poly_match": [int(x) for x in got["final_poly"]] == [int(x) for x in ref["final_poly"]],
+                "fri_commits_match": (got.get("commits") == ref["commits"]) if got.get("commits") is not None else None,
+            }
+            if not (self_check["root_match"] and self_check["final_poly_match"]):
+                raise SystemExit(f"bench.py: self-check FAILED against the oracle: {self_check}")
+    runner = make_runner(a.log_rows)
 
     def barrier():
         if world > 1:
@@ -342,7 +381,9 @@ def run_b200(a):
                           "achieved_GBs": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) if lde_ms else None,
                           "frac_of_hbm_peak": alg["lde_stage_5B_per_elem"] / 1e9 / (lde_ms * 1e-3) / peak if lde_ms else None,
                           "int32": int32},
-            "result": {"root": last["root"].hex() if last else None, "final_poly": last["final_poly"] if last else None},
+            "result": {"root": last["root"].hex() if last else None, "final_poly": last["final_poly"] if last else None,
+                       "trace": f"SplitMix64 seed {a.seed} (oracle.splitmix_matrix): identical at every N"},
+            "self_check": self_check,
         }
         if not a.no_cpu_baseline and world == 1:
             cb = cpu_sample(a, 1, 0)
@@ -357,16 +398,16 @@ def run_b200(a):
 class SingleGpuRunner:
     parallelism = "1 GPU"
 
-    def __init__(self, ts, ctx, log_rows, width, log_blowup):
+    def __init__(self, ts, ctx, log_rows, width, log_blowup, seed=0):
         import torch
 
         self.ts, self.ctx, self.torch = ts, ctx, torch
         self.log_rows, self.width, self.b = log_rows, width, log_blowup
         n = 1 << log_rows
-        g = torch.Generator(device="cuda")
-        g.manual_seed(1234)
-        # any u32 < p is a valid Montgomery-form BabyBear element
-        self.trace_t = torch.randint(0, P, (n, width), dtype=torch.int32, device="cuda", generator=g)
+        # element (r, c) = SplitMix64((seed << 40) + r*width + c) mod p, generated on the device in
+        # Montgomery form -- the matrix oracle.splitmix_matrix(seed, n, width) holds in canonical form
+        self.trace_t = torch.empty((n, width), dtype=torch.int32, device="cuda")
+        ctx.check(ctx._L.ts_fill_splitmix(ctx._h, self.trace_t.data_ptr(), n, width, seed, 0, width, 1), "fill_splitmix")
         self.trace = ts.DeviceMatrix.wrap_device(ctx, self.trace_t.data_ptr(), n, width, keepalive=self.trace_t)
         mm = ts.Blake3MerkleMmcs(ctx)
         self.pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(log_blowup, 16, 8, mm))
@@ -385,7 +426,7 @@ class SingleGpuRunner:
         res = ts.bf_commit_phase(self.pcs.fri, [fri_in], ch, keep_data=False)
         fri_in.free()
         data.free()
-        return {"root": root, "rounds": len(res.commits), "final_poly": res.final_poly.tolist()}
+        return {"root": root, "rounds": len(res.commits), "final_poly": res.final_poly.tolist(), "commits": list(res.commits)}
 
     def step_resident(self):
         root, data = self.pcs.commit([(self.dom, self.trace)])

@@ -224,6 +224,13 @@ int ts_interpolate_low_coset(ts_ctx *ctx, const ts_matrix *lde, size_t n, const 
 int ts_reduce_opening_acc(ts_ctx *ctx, const ts_matrix *dot, const ts_matrix *inv_denoms,
                           const uint32_t alpha_pow_offset_monty[4], const uint32_t reduced_ys_monty[4], ts_matrix *ro);
 int ts_matrix_zero(ts_ctx *ctx, ts_matrix *m);
+/* Synthetic inputs (the reference's tests draw theirs from `RowMajorMatrix::rand(&mut rng, ..)`, fri/tests/pcs.rs,
+ * fri/src/fold_even_odd.rs:70; that ChaCha stream cannot be reproduced without the rand crates):
+ * fills the rows x width device buffer `dev` with columns [col0, col0+width) of the rows x total_width matrix whose
+ * element (r, c) is SplitMix64((seed << 40) + r*total_width + c) mod p -- a pure function of (seed, r, c), so every rank of
+ * a column-sharded run and the CPU oracle (oracle.splitmix_matrix) hold the same trace.  monty != 0: Montgomery form. */
+int ts_fill_splitmix(ts_ctx *ctx, uint32_t *dev, size_t rows, size_t width, uint64_t seed, size_t col0,
+                     size_t total_width, int monty);
 
 /* ---------------------------------------------------------------- sharded building blocks (one process per GPU)
  * The path shards as SURVEY 8(e): LDE by columns (no communication), one all-to-all to re-shard by rows,

@@ -97,6 +97,9 @@ def lib():
         "or_chal_grind": (C.c_uint32, [C.POINTER(Challenger), C.c_uint, C.c_int]),
         "or_fri_commit_phase": (C.c_int, [C.POINTER(u32p), szp, C.c_size_t, C.c_uint, C.POINTER(Challenger), u8p, u32p, C.POINTER(u32p), u32p]),
         "or_num_threads": (C.c_int, []),
+        "or_set_num_threads": (None, [C.c_int]),
+        "or_splitmix_fill": (None, [u32p, C.c_size_t, C.c_uint64]),
+        "or_merkle_root_from_leaves": (None, [u8p, C.c_size_t, u8p]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -150,6 +153,10 @@ def ef_mul(a, b) -> np.ndarray:
 # ----------------------------------------------------------------------------- synthetic inputs
 def splitmix_matrix(seed: int, rows: int, width: int) -> np.ndarray:
     """Counter-based synthetic trace: element i = SplitMix64(seed*2^40 + i) mod p, canonical."""
+    if rows * width >= 1 << 24:  # big traces: the C loop (bit-identical; tests/test_oracle_pins.py compares the two)
+        out = np.empty((rows, width), dtype=np.uint32)
+        lib().or_splitmix_fill(_u32p(out), rows * width, seed)
+        return out
     idx = np.arange(rows * width, dtype=np.uint64) + (np.uint64(seed) << np.uint64(40))
     with np.errstate(over="ignore"):
         z = idx + np.uint64(0x9E3779B97F4A7C15)
@@ -268,6 +275,41 @@ class Tree:
 
 def mmcs_commit(mats, layout=LAYOUT_P3_INJECT) -> Tree:
     return Tree(mats, layout)
+
+
+def mmcs_verify_batch(heights, rows, index: int, path, root: bytes, layout=LAYOUT_P3_INJECT) -> bool:
+    """basic/src/mmcs/bf_mmcs.rs:54-62 verify_batch without a Tree object: heights of the committed matrices, the
+    opened rows (canonical), the authentication path and the root."""
+    k = len(heights)
+    hs = (C.c_size_t * k)(*heights)
+    ws = (C.c_size_t * k)(*[len(r) for r in rows])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.uint32) for r in rows]))
+    path = np.ascontiguousarray(path, dtype=np.uint8)
+    depth = path.shape[0] if path.size else 0
+    pbuf = path.reshape(-1) if path.size else np.zeros(32, dtype=np.uint8)
+    r = np.frombuffer(root, dtype=np.uint8).copy()
+    return bool(lib().or_mmcs_verify_batch(hs, ws, k, layout, index, _u32p(flat), _u8p(pbuf), depth, _u8p(r)))
+
+
+def merkle_root_from_leaves(leaves: np.ndarray) -> bytes:
+    """Root of the 2-to-1 Blake3 tree over a power-of-two number of 32-byte leaf digests ([n, 32] uint8)."""
+    leaves = np.ascontiguousarray(leaves, dtype=np.uint8).reshape(-1, 32)
+    log2_strict(leaves.shape[0])
+    root = np.zeros(32, dtype=np.uint8)
+    lib().or_merkle_root_from_leaves(_u8p(leaves), leaves.shape[0], _u8p(root))
+    return root.tobytes()
+
+
+def splitmix_columns(seed: int, rows: int, total_width: int, cols) -> np.ndarray:
+    """Columns `cols` of splitmix_matrix(seed, rows, total_width) without materialising the matrix."""
+    idx = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(total_width) + np.asarray(cols, dtype=np.uint64)[None, :]
+           + (np.uint64(seed) << np.uint64(40)))
+    with np.errstate(over="ignore"):
+        z = idx + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z % np.uint64(P)).astype(np.uint32)
 
 
 def padded_leaf(mats, leaf: int) -> np.ndarray:
@@ -396,3 +438,16 @@ def fri_commit_phase(inputs, log_blowup: int, chal: BfChallenger, want_layers: b
 
 def num_threads() -> int:
     return lib().or_num_threads()
+
+
+def use_all_cores() -> int:
+    """Sets the OpenMP team to every core this process may run on (torch.distributed.run exports
+    OMP_NUM_THREADS=1, which would otherwise turn the multi-core CPU arm of bench.py into a 1-core run)."""
+    import os
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().or_set_num_threads(n)
+    return num_threads()

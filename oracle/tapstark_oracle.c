@@ -23,6 +23,29 @@ int or_num_threads(void) {
 #endif
 }
 
+/* SURVEY 8(d) synthetic trace: element i = SplitMix64((seed << 40) + i) mod p, canonical (same as oracle.py splitmix_matrix;
+ * here so that a 2^22 x 256 trace does not go through several 8 GiB numpy temporaries). */
+void or_splitmix_fill(uint32_t *out, size_t count, uint64_t seed) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < count; i++) {
+        uint64_t z = (seed << 40) + (uint64_t)i + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        out[i] = (uint32_t)(z % P);
+    }
+}
+
+/* bench.py's CPU arm sets the thread count explicitly: under torch.distributed.run the environment carries
+ * OMP_NUM_THREADS=1, which would silently time the port on one core. */
+void or_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ============================== BabyBear ============================================= */
 /* basic/src/field/mod.rs:43-51 (MOD = 0x78000001); arithmetic is [MEM] p3-baby-bear, exact mod p. */
 uint32_t or_bb_add(uint32_t a, uint32_t b) {
@@ -479,6 +502,25 @@ const uint8_t *or_tree_layer(const or_tree *t, size_t layer, size_t *len) {
     if (len) *len = t->layer_len[layer];
     return t->layers[layer];
 }
+/* Root of the plain 2-to-1 tree over n = 2^k given leaf digests (parent = blake3(left || right), [MEM]
+ * CompressionFunctionFromHasher): lets a test rebuild the top of a commitment from a leaf layer that was produced
+ * elsewhere (the device) without re-hashing 16 GiB of rows on the CPU. */
+void or_merkle_root_from_leaves(const uint8_t *leaves, size_t n, uint8_t root[32]) {
+    uint8_t *cur = (uint8_t *)malloc(32 * n);
+    memcpy(cur, leaves, 32 * n);
+    while (n > 1) {
+        const size_t half = n / 2;
+        uint8_t *nxt = (uint8_t *)malloc(32 * half);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < half; i++) compress2(cur + 64 * i, cur + 64 * i + 32, nxt + 32 * i);
+        free(cur);
+        cur = nxt;
+        n = half;
+    }
+    memcpy(root, cur, 32);
+    free(cur);
+}
+
 void or_mmcs_open_batch(const or_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out) {
     /* [MEM] FieldMerkleTreeMmcs::open_batch; same index semantics as basic/src/mmcs/bf_mmcs.rs:11-16 */
     unsigned lmax = log2_strict(t->heights[t->order[0]]);

@@ -123,6 +123,9 @@ int or_fri_commit_phase(const uint32_t *const *inputs, const size_t *lens, size_
                         uint32_t final_poly[4], uint32_t **layers_out, uint32_t *betas_out);
 
 int or_num_threads(void);
+void or_set_num_threads(int n);
+void or_splitmix_fill(uint32_t *out, size_t count, uint64_t seed);
+void or_merkle_root_from_leaves(const uint8_t *leaves, size_t n, uint8_t root[32]);
 
 #ifdef __cplusplus
 }

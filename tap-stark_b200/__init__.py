@@ -110,6 +110,7 @@ _SIGNATURES = {
     "ts_interpolate_low_coset": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "ts_reduce_opening_acc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "ts_matrix_zero": (C.c_int, [_vp, _vp]),
+    "ts_fill_splitmix": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_uint64, C.c_size_t, C.c_size_t, C.c_int]),
     "ts_coset_lde_batch_into": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint32, _vp]),
     "ts_alpha_powers": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
     "ts_dot_ext_powers_acc": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_int]),
@@ -256,6 +257,18 @@ class DeviceMatrix:
         h = C.c_void_p()
         ctx.check(ctx._L.ts_matrix_wrap_device(ctx._h, C.c_void_p(dev_ptr), rows, width, C.byref(h)), "wrap")
         return cls(ctx, h, keepalive=keepalive)
+
+    @classmethod
+    def splitmix(cls, ctx: Context, seed: int, rows: int, width: int, col0: int = 0, total_width: Optional[int] = None,
+                 monty: bool = True) -> "DeviceMatrix":
+        """Columns [col0, col0+width) of the synthetic rows x total_width trace of SURVEY 8(d), generated on the device
+        (ts_fill_splitmix): the same matrix as oracle.splitmix_matrix(seed, rows, total_width), in Montgomery form."""
+        h = C.c_void_p()
+        ctx.check(ctx._L.ts_matrix_alloc(ctx._h, rows, width, C.byref(h)), "matrix_alloc")
+        m = cls(ctx, h)
+        ctx.check(ctx._L.ts_fill_splitmix(ctx._h, C.c_void_p(m.device_ptr), rows, width, seed, col0,
+                                          width if total_width is None else total_width, 1 if monty else 0), "fill_splitmix")
+        return m
 
     # accessors ---------------------------------------------------------------------------------
     @property

@@ -407,6 +407,23 @@ __global__ void broadcast_row_kernel(const uint32_t *in, uint32_t *out, size_t r
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
         out[i] = in[i % width];
 }
+// synthetic trace: element (r, c) of a rows x total_width matrix = SplitMix64((seed << 40) + r * total_width + c)
+// mod p; this kernel fills the column window [col0, col0 + width) of it, so every rank of a column-sharded run holds
+// its slice of the SAME matrix.  Same function as oracle.splitmix_matrix.
+__global__ void fill_splitmix_kernel(uint32_t *out, size_t rows, uint32_t width, uint64_t seed, uint32_t col0,
+                                     uint32_t total_width, int monty) {
+    const size_t total = rows * width;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / width;
+        const uint32_t c = (uint32_t)(i % width);
+        uint64_t z = (seed << 40) + (uint64_t)r * total_width + col0 + c + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const uint32_t v = (uint32_t)(z % bb::P);
+        out[i] = monty ? bb::to_monty(v) : v;
+    }
+}
 __global__ void monty_convert_kernel(uint32_t *data, size_t n, int to) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         data[i] = to ? bb::to_monty(data[i]) : bb::from_monty(data[i]);

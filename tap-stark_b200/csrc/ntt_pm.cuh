@@ -73,22 +73,40 @@ TS_D V4 vmul2(const V4 &a, uint2 w1, uint2 w2) {
     return r;
 }
 
-// radix-2^LOGR DIF DFT on R quads, compile-time twiddles; natural in, register i holds frequency brev(i)
-template <int LOGR, bool INV>
+// unreduced sum / difference for operands of a Shoup multiplication (which takes any u32): a + b < 2p, a - b + p < 2p
+TS_D V4 vadd_raw(const V4 &a, const V4 &b) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = a.v[k] + b.v[k];
+    return r;
+}
+TS_D V4 vsub_raw(const V4 &a, const V4 &b) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = a.v[k] - b.v[k] + bb::P;
+    return r;
+}
+
+// radix-2^LOGR DIF DFT on R quads, compile-time twiddles; natural in, register i holds frequency brev(i).
+// LAZY: the caller multiplies every output register >= LAZY_FROM by a twiddle next, so the last stage leaves those
+// outputs unreduced in [0, 2p) (one instruction per sum / difference instead of two).
+template <int LOGR, bool INV, bool LAZY = false, int LAZY_FROM = 1>
 TS_D void dft_v4(V4 (&x)[1 << LOGR]) {
     constexpr bb::InnerTw<LOGR, INV> T{};
     constexpr int R = 1 << LOGR;
     TS_UNROLL
     for (int s = 0; s < LOGR; s++) {
         const int half = R >> (s + 1);
+        const bool last = LAZY && s == LOGR - 1;
         TS_UNROLL
         for (int blk = 0; blk < R; blk += 2 * half) {
             TS_UNROLL
             for (int j = 0; j < half; j++) {
                 const V4 a = x[blk + j], b = x[blk + j + half];
-                x[blk + j] = vadd(a, b);
+                x[blk + j] = (last && blk + j >= LAZY_FROM) ? vadd_raw(a, b) : vadd(a, b);
                 const int e = j << s;
-                x[blk + j + half] = e == 0 ? vsub(a, b) : vsubmul(a, b, T.w[e], T.wp[e]);
+                x[blk + j + half] = e == 0 ? ((last && blk + j + half >= LAZY_FROM) ? vsub_raw(a, b) : vsub(a, b))
+                                           : vsubmul(a, b, T.w[e], T.wp[e]);
             }
         }
     }
@@ -132,7 +150,7 @@ TS_D void dif_r1(const uint4 *src, uint4 *dst, const FastTables &t, const uint2 
             TS_UNROLL
             for (int c = 0; c < R; c++) x[c] = vmul2(x[c], __ldg(pre_tab + g + 256 * c), lw);
         }
-        dft_v4<LOGR, INV>(x);
+        dft_v4<LOGR, INV, true>(x);
         TS_UNROLL
         for (int i = 1; i < R; i++) x[i] = vmul(x[i], rtw<INV, SM, D, 8>(t, sm_tab, g, (uint32_t)brev_c(i, LOGR), i));
         TS_UNROLL
@@ -151,7 +169,7 @@ TS_D void dif_r2(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
         V4 x[8];
         TS_UNROLL
         for (int c = 0; c < 8; c++) x[c] = ld4(tile + ((c & 1) ? b1 : b0) + 32 * c);
-        dft_v4<3, INV>(x);
+        dft_v4<3, INV, true>(x);
         TS_UNROLL
         for (int i = 1; i < 8; i++) x[i] = vmul(x[i], rtw<INV, SM, 8, 5>(t, sm_tab, g, (uint32_t)brev_c(i, 3), i));
         TS_UNROLL
@@ -170,7 +188,7 @@ TS_D void dif_r3(uint4 *tile, const FastTables &t, const uint2 *sm_tab, int tid)
         V4 x[8];
         TS_UNROLL
         for (int c = 0; c < 8; c++) x[c] = ld4(tile + (base ^ (uint32_t)((4 * c) ^ ((c >> 1) & 3))));
-        dft_v4<3, INV>(x);
+        dft_v4<3, INV, true>(x);
         TS_UNROLL
         for (int i = 1; i < 8; i++) x[i] = vmul(x[i], rtw<INV, SM, 5, 2>(t, sm_tab, g, (uint32_t)brev_c(i, 3), i));
         TS_UNROLL
@@ -375,7 +393,7 @@ TS_D void dif_r1_ld(uint4 *tile, const uint32_t *src, size_t row_base, size_t ro
                                 : make_uint4(0, 0, 0, 0);
             x[c] = V4{{v.x, v.y, v.z, v.w}};
         }
-        dft_v4<LOGR, INV>(x);
+        dft_v4<LOGR, INV, true>(x);
         TS_UNROLL
         for (int i = 1; i < R; i++) x[i] = vmul(x[i], rtw<INV, false, D, 8>(t, nullptr, g, (uint32_t)brev_c(i, LOGR), i));
         const uint32_t b0 = hx<D>(h) ^ sigma(g);

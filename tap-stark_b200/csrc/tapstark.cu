@@ -20,6 +20,7 @@
 #include "ntt.cuh"
 #include "ntt_fast.cuh"
 #include "ntt_pm.cuh"
+#include "ntt_v4.cuh"
 #include "open.cuh"
 #include "quotient.cuh"
 
@@ -44,6 +45,12 @@ struct ts_ctx {
     int big_log = 0;
     uint32_t *fold_tlo = nullptr;
     std::map<std::tuple<int, int, int, uint32_t>, std::pair<uint2 *, uint2 *>> coset_tabs;
+    // ntt_v4.cuh tables: inverse inter-digit twiddles [lo][p] per (m, top digit); per (m, b, low digit, shift) the forward
+    // top-digit twiddles with the coset scalars folded in [j][Kc][p] and the coset powers [j][g][c]
+    std::map<std::pair<int, int>, uint2 *> v4_post1;
+    struct V4Mid { uint2 *post3 = nullptr, *pre4 = nullptr; uint64_t stamp = 0; };
+    std::map<std::tuple<int, int, int, uint32_t>, V4Mid> v4_mid;
+    uint64_t v4_clock = 0;
     uint32_t *scratch = nullptr;
     size_t scratch_words = 0;
     // stream-ordered caching allocator: freed blocks are reused by later work on the same stream without a
@@ -469,6 +476,9 @@ bool all_digits_fast(int m, size_t w) {
     return true;
 }
 
+bool v4_shape(int m, size_t w);
+int lde_committed_v4(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty, uint32_t *dst,
+                     size_t src_pitch, size_t dst_pitch);
 // windows: src is n x w with row stride src_pitch, dst is (n<<b) x w with row stride dst_pitch (0 = w)
 int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty,
                   uint32_t *dst, size_t src_pitch = 0, size_t dst_pitch = 0, const PeerDst *peers = nullptr) {
@@ -485,6 +495,7 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         TS_LAUNCH(kfn, 64, 256, 0, c->stream, src, dst, (size_t)1 << b, (uint32_t)w);
         return check_launch(c, "broadcast_row_kernel");
     }
+    if (!peers && v4_shape(m, w)) return lde_committed_v4(c, src, n, w, b, shift_monty, dst, src_pitch, dst_pitch);
     const std::vector<int> dg = split_digits(m);
     const size_t D = dg.size();
     const int dK = dg[D - 1];
@@ -622,6 +633,154 @@ int lde_committed(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b
         used += dg[i];
     }
     if (inter) pool_release(c, inter);  // stream-ordered: later allocations on this stream may reuse it
+    return rc;
+}
+
+// ---- ntt_v4.cuh: two-digit LDE as four launches of one pass kernel ---------------------------------------------------
+bool use_v4() {
+    static const bool off = getenv("TS_NO_V4") != nullptr;
+    return !off;
+}
+bool v4_shape(int m, size_t w) {
+    if (!use_v4() || !use_pm() || getenv("TS_NO_BLOCKED")) return false;
+    const std::vector<int> dg = split_digits(m);
+    return dg.size() == 2 && all_digits_fast(m, w);
+}
+template <int D>
+int launch_v4(ts_ctx *c, int kind, const ntt4::PassParams &p, size_t blocks) {  // kind: 1..4 = P1..P4 (ntt_v4.cuh)
+    const size_t smem = (size_t)16384 * 4;
+    KScope ks(c, kind == 3 ? TS_K_LDE_MID : TS_K_NTT_PASS);
+    if (kind == 1) {
+        auto kfn = ntt4::pass_kernel<D, true, false, false>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+    } else if (kind == 2) {
+        auto kfn = ntt4::pass_kernel<D, true, false, true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+    } else if (kind == 3) {
+        auto kfn = ntt4::pass_kernel<D, false, true, true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+    } else {
+        auto kfn = ntt4::pass_kernel<D, false, false, true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+    }
+    return check_launch(c, "ntt4::pass_kernel");
+}
+int launch_v4_d(ts_ctx *c, int d, int kind, ntt4::PassParams &p, size_t tiles) {
+    const size_t K = (size_t)1 << (14 - d);
+    p.n_col_slices = (uint32_t)((p.ncols + K - 1) / K);
+    p.cs_shift = log2_strict(p.n_col_slices);
+    p.t = fast_tables(c);
+    const size_t blocks = tiles * p.n_col_slices;
+    switch (d) {
+        case 9: return launch_v4<9>(c, kind, p, blocks);
+        case 10: return launch_v4<10>(c, kind, p, blocks);
+        default: return launch_v4<11>(c, kind, p, blocks);
+    }
+}
+int v4_get_post1(ts_ctx *c, int m, int d0, uint2 **out) {
+    auto key = std::make_pair(m, d0);
+    auto it = c->v4_post1.find(key);
+    if (it != c->v4_post1.end()) {
+        *out = it->second;
+        return TS_OK;
+    }
+    uint2 *t = nullptr;
+    TS_CUDA(c, cudaMalloc((void **)&t, sizeof(uint2) << m));
+    {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = ntt4::fill_post_table_kernel;
+        TS_LAUNCH(kfn, (unsigned)((((size_t)1 << m) + 255) / 256), 256, 0, c->stream, t, c->tw_big, c->big_log, m, d0, m - d0, 1);
+    }
+    TS_TRY(check_launch(c, "fill_post_table_kernel"));
+    c->v4_post1[key] = t;
+    *out = t;
+    return TS_OK;
+}
+int v4_get_mid(ts_ctx *c, int m, int b, int dK, uint32_t shift_monty, uint2 **post3, uint2 **pre4) {
+    auto key = std::make_tuple(m, b, dK, shift_monty);
+    auto it = c->v4_mid.find(key);
+    if (it != c->v4_mid.end()) {
+        it->second.stamp = ++c->v4_clock;
+        *post3 = it->second.post3;
+        *pre4 = it->second.pre4;
+        return TS_OK;
+    }
+    // a prover commits a handful of (size, shift) pairs per proof (trace + quotient chunks); beyond 12 cached shapes the
+    // least recently used tables go back to the pool (stream-ordered, so work already queued on them is safe)
+    while (c->v4_mid.size() >= 12) {
+        auto old = c->v4_mid.begin();
+        for (auto q = c->v4_mid.begin(); q != c->v4_mid.end(); ++q)
+            if (q->second.stamp < old->second.stamp) old = q;
+        pool_release(c, old->second.post3);
+        pool_release(c, old->second.pre4);
+        c->v4_mid.erase(old);
+    }
+    uint2 *pre, *lane;
+    TS_TRY(get_coset_tables(c, m, b, dK, shift_monty, &pre, &lane));
+    const int klo = m - dK;
+    ts_ctx::V4Mid t;
+    TS_CUDA(c, pool_alloc(c, (void **)&t.post3, sizeof(uint2) << (m + b)));
+    TS_CUDA(c, pool_alloc(c, (void **)&t.pre4, sizeof(uint2) << (dK + b)));
+    {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = ntt4::fill_mid_post_table_kernel;
+        TS_LAUNCH(kfn, (unsigned)((((size_t)1 << (m + b)) + 255) / 256), 256, 0, c->stream, t.post3, c->tw_big, lane, c->big_log, m,
+                  dK, klo, b);
+    }
+    TS_TRY(check_launch(c, "fill_mid_post_table_kernel"));
+    {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = ntt4::fill_pre_table_kernel;
+        TS_LAUNCH(kfn, ((1u << (dK + b)) + 255) / 256, 256, 0, c->stream, t.pre4, pre, dK, b);
+    }
+    TS_TRY(check_launch(c, "fill_pre_table_kernel"));
+    t.stamp = ++c->v4_clock;
+    c->v4_mid[key] = t;
+    *post3 = t.post3;
+    *pre4 = t.pre4;
+    return TS_OK;
+}
+// dst (n << b) x w  <-  committed-order coset LDE of src (n x w); windows as in lde_committed
+int lde_committed_v4(ts_ctx *c, const uint32_t *src, size_t n, size_t w, unsigned b, uint32_t shift_monty, uint32_t *dst,
+                     size_t src_pitch, size_t dst_pitch) {
+    const int m = log2_strict(n);
+    const std::vector<int> dg = split_digits(m);
+    const int d0 = dg[0], dK = dg[1], klo = m - dK;
+    const size_t w8 = (w + 7) & ~(size_t)7, N = n << b;
+    const size_t s_slice = n * 8, i_slice = N * 8;
+    TS_TRY(ensure_big(c, m));
+    TS_TRY(ensure_scratch(c, n * w8));
+    uint2 *post1, *post3, *pre4;
+    TS_TRY(v4_get_post1(c, m, d0, &post1));
+    TS_TRY(v4_get_mid(c, m, (int)b, dK, shift_monty, &post3, &pre4));
+    uint32_t *inter = nullptr;
+    TS_CUDA(c, pool_alloc(c, (void **)&inter, N * w8 * 4));
+    int rc;
+    {  // P1: inverse, top digit; caller's rows -> blocked scratch
+        ntt4::PassParams p;
+        p.src = src, p.dst = c->scratch, p.src_pitch = (uint32_t)src_pitch, p.dst_pitch = (uint32_t)w, p.ncols = (uint32_t)w;
+        p.src_slice = 0, p.dst_slice = s_slice, p.lo_bits = m - d0, p.hi_bits = 0, p.post = post1;
+        rc = launch_v4_d(c, d0, 1, p, (size_t)1 << (m - d0));
+    }
+    if (rc == TS_OK) {  // P2: inverse, low digit, in place (bit-reversed coefficient order, unscaled)
+        ntt4::PassParams p;
+        p.src = c->scratch, p.dst = c->scratch, p.src_pitch = p.dst_pitch = (uint32_t)w, p.ncols = (uint32_t)w;
+        p.src_slice = p.dst_slice = s_slice, p.lo_bits = 0, p.hi_bits = m - dK;
+        rc = launch_v4_d(c, dK, 2, p, (size_t)1 << (m - dK));
+    }
+    if (rc == TS_OK) {  // P3: forward, top digit, once per coset
+        ntt4::PassParams p;
+        p.src = c->scratch, p.dst = inter, p.src_pitch = p.dst_pitch = (uint32_t)w, p.ncols = (uint32_t)w;
+        p.src_slice = s_slice, p.dst_slice = i_slice, p.klo_bits = klo, p.b = (int)b, p.m = m, p.post = post3, p.pre = pre4;
+        rc = launch_v4_d(c, dK, 3, p, (size_t)1 << (klo + b));
+    }
+    if (rc == TS_OK) {  // P4: forward, low digit; blocked intermediate -> caller's rows in committed order
+        ntt4::PassParams p;
+        p.src = inter, p.dst = dst, p.src_pitch = (uint32_t)w, p.dst_pitch = (uint32_t)dst_pitch, p.ncols = (uint32_t)w;
+        p.src_slice = i_slice, p.dst_slice = 0, p.lo_bits = klo - d0, p.hi_bits = m + (int)b - klo;
+        rc = launch_v4_d(c, d0, 4, p, (size_t)1 << (m + b - d0));
+    }
+    pool_release(c, inter);
     return rc;
 }
 
@@ -1071,6 +1230,18 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<9, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<9, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<9, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<9, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<10, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<10, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<10, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<10, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<11, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<11, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<11, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_kernel<11, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
@@ -1150,6 +1321,11 @@ void ts_ctx_destroy(ts_ctx *c) {
         cudaStreamDestroy(c->copy_stream);
     }
 #endif
+    for (auto &kv : c->v4_post1) cudaFree(kv.second);
+    for (auto &kv : c->v4_mid) {
+        pool_release(c, kv.second.post3);
+        pool_release(c, kv.second.pre4);
+    }
     pool_trim(c);
     for (auto &kv : c->coset_tabs) {
         cudaFree(kv.second.first);
@@ -2086,6 +2262,16 @@ int ts_reduce_opening_acc(ts_ctx *c, const ts_matrix *dot, const ts_matrix *inv_
               (const uint4 *)dot->d, (const uint4 *)inv_denoms->d, to_e4(alpha_pow_offset_monty), to_e4(reduced_ys_monty), h,
               (uint4 *)ro->d);
     return check_launch(c, "reduce_rows_kernel");
+}
+int ts_fill_splitmix(ts_ctx *c, uint32_t *dev, size_t rows, size_t width, uint64_t seed, size_t col0, size_t total_width,
+                     int monty) {
+    if (!c || !dev || width == 0 || col0 + width > total_width || total_width > 0xffffffffu) TS_FAIL(c, TS_ERR_ARG, "fill_splitmix: bad window");
+    KScope ks(c, TS_K_MISC);
+    auto kfn = ntt::fill_splitmix_kernel;
+    const size_t total = rows * width;
+    TS_LAUNCH(kfn, (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream, dev, rows,
+              (uint32_t)width, seed, (uint32_t)col0, (uint32_t)total_width, monty);
+    return check_launch(c, "fill_splitmix_kernel");
 }
 int ts_matrix_zero(ts_ctx *c, ts_matrix *m) {
     TS_CUDA(c, cudaMemsetAsync(m->d, 0, m->rows * m->width * 4, c->stream));

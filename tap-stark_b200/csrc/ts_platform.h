@@ -13,6 +13,7 @@
     ts_emul::launch(dim3(grid), dim3(block), (smem), [=]() { kfn(__VA_ARGS__); })
 #define TS_UNROLL
 #define TS_UNROLL2
+#define TS_NOUNROLL
 #else
 #include <cuda_runtime.h>
 #define TS_DYN_SMEM(type, name)                                   \
@@ -20,6 +21,7 @@
     type *name = reinterpret_cast<type *>(name##_raw_)
 #define TS_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TS_UNROLL _Pragma("unroll")
+#define TS_NOUNROLL _Pragma("unroll 1")
 #ifndef TS_NO_LANE_UNROLL2
 #define TS_UNROLL2 _Pragma("unroll 2")
 #else

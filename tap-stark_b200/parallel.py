@@ -316,7 +316,7 @@ class ShardedProver:
 class ShardedRunner:
     """bench.py driver for N > 1 (strong scaling: the 2^log_rows x width trace is split by columns)."""
 
-    def __init__(self, ts, ctx, log_rows, width, log_blowup, rank, world):
+    def __init__(self, ts, ctx, log_rows, width, log_blowup, rank, world, seed=0):
         import torch
 
         self.ts, self.ctx, self.torch = ts, ctx, torch
@@ -325,9 +325,11 @@ class ShardedRunner:
             raise ts.TapStarkError("width must be divisible by the number of GPUs")
         self.n, self.wl, self.b = 1 << log_rows, width // world, log_blowup
         dev = torch.device("cuda", torch.cuda.current_device())
-        g = torch.Generator(device="cuda")
-        g.manual_seed(1234 + rank)
-        self.trace_t = torch.randint(0, ts.P, (self.n, self.wl), dtype=torch.int32, device="cuda", generator=g)
+        # this rank's columns [rank*wl, (rank+1)*wl) of the ONE synthetic trace every N works on (element
+        # (r, c) = SplitMix64((seed << 40) + r*width + c) mod p), so root and final polynomial are the 1-GPU ones
+        self.trace_t = torch.empty((self.n, self.wl), dtype=torch.int32, device="cuda")
+        ctx.check(ctx._L.ts_fill_splitmix(ctx._h, self.trace_t.data_ptr(), self.n, self.wl, seed, rank * self.wl, width, 1),
+                  "fill_splitmix")
         self.prover = ShardedProver(ts, ctx, rank, world, log_blowup, dev)
         self.parallelism = (f"{world} GPUs: LDE column-sharded ({self.wl} cols/GPU), NCCL all-to-all re-shard by rows, "
                             f"row-sharded Blake3 subtrees + FRI folding, 32-byte sub-root all-gathers")

@@ -276,6 +276,80 @@ def test_config4_full_height_properties(ts, ctx, orc):
         mm.verify_batch([1 << 23], rows, idx, path, root)
 
 
+def _replay_query_path(ts, orc, cfg, res, log_len, idx, rch=None):
+    """Host replay of one FRI query path (fold_row, two_adic_pcs.rs:87-114) over the opened layer rows: betas from the
+    commitments, every opening verified against its layer commitment, the last folded value = final_poly.  rch: an
+    oracle challenger in the state the commit phase started from."""
+    rch = rch if rch is not None else orc.BfChallenger()
+    folded = None
+    for r, (commit, pd) in enumerate(zip(res.commits, res.data)):
+        rch.observe_digest(commit)
+        beta = rch.sample_ef()
+        pair = idx >> 1
+        rows, path = cfg.mmcs.open_batch(pair, pd)
+        cfg.mmcs.verify_batch([1 << (log_len - 1 - r)], rows, pair, path, commit)
+        e0, e1 = rows[0][:4], rows[0][4:]
+        if folded is not None:
+            assert np.array_equal(folded, e1 if idx & 1 else e0)
+        folded = orc.fold_row_ef(pair, log_len - 1 - r, beta, e0, e1)
+        idx = pair
+    assert np.array_equal(folded, res.final_poly)
+
+
+def test_config3_full_size(ts, ctx, orc):
+    """BASELINE config 3 = the bench workload at its own size (2^22 x 256 SplitMix trace, log_blowup 2), one GPU:
+      * the device trace generator against the oracle's definition (column subset);
+      * LDE (two_adic_pcs.rs:237-240): a column subset against the oracle LDE at three row windows;
+      * leaf digests of sampled rows = Blake3 of the row's canonical LE bytes (orc.blake3), >= 8 openings verified by the
+        ORACLE's verify_batch against the device root;
+      * root = the oracle's 2-to-1 tree over the device's 2^24-leaf layer;
+      * alpha-reduction on sampled rows against big-int arithmetic, then the FRI commit phase (prover.rs:93-141) replayed
+        along two query paths with the oracle's fold_row, ending in the device's final polynomial."""
+    log_n, w, b, seed = 22, 256, 2, 0
+    n, N = 1 << log_n, 1 << (log_n + b)
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(b, 16, 8, mm))
+    ev = ts.DeviceMatrix.splitmix(ctx, seed, n, w)
+    cols = [0, 9, 130, 255]
+    host_cols = orc.splitmix_columns(seed, n, w, cols)
+    for r0 in (0, n - 1024, 1234567):
+        assert np.array_equal(ev.to_canonical(r0, 1024)[:, cols], host_cols[r0 : r0 + 1024])
+    root, data = pcs.commit([(pcs.natural_domain_for_degree(n), ev)])
+    lde = mm.get_matrices(data)[0]
+    want = orc.pcs_lde_committed(host_cols, b)
+    for r0 in (0, N - 4096, 5 << 21):
+        assert np.array_equal(lde.to_canonical(r0, 4096)[:, cols], want[r0 : r0 + 4096])
+    leaves = data.layer(0)
+    assert leaves.shape == (N, 32)
+    assert orc.merkle_root_from_leaves(leaves) == root
+    rng = np.random.default_rng(3)
+    sample = [0, 1, N - 1] + [int(x) for x in rng.integers(0, N, 7)]
+    for idx in sample:
+        rows, path = mm.open_batch(idx, data)
+        assert np.array_equal(rows[0][cols], want[idx])
+        assert orc.blake3(rows[0].astype("<u4").tobytes()) == leaves[idx].tobytes()
+        assert orc.mmcs_verify_batch([N], rows, idx, path, root)
+    # alpha-reduction + FRI commit phase, as bench.py runs them
+    ch = ts.BfChallenger()
+    ch.observe(root)
+    alpha = ch.sample()
+    och = orc.BfChallenger()
+    och.observe_digest(root)
+    assert np.array_equal(np.asarray(och.sample_ef(), dtype=np.uint32), np.asarray(alpha, dtype=np.uint32))
+    fri_in = pcs.dot_ext_powers(lde, alpha)
+    for idx in sample[:4]:
+        row = lde.to_canonical(idx, 1)[0]
+        acc, apow = np.zeros(4, dtype=np.uint32), np.array([1, 0, 0, 0], dtype=np.uint32)
+        for c in range(w):
+            acc = (acc.astype(np.uint64) + apow.astype(np.uint64) * int(row[c])) % P
+            apow = orc.ef_mul(apow, np.asarray(alpha, dtype=np.uint32))
+        assert np.array_equal(fri_in.to_canonical(idx, 1)[0], acc.astype(np.uint32))
+    res = ts.bf_commit_phase(pcs.fri, [fri_in], ch)
+    assert len(res.commits) == log_n
+    for idx in (987654321 % N, 3):
+        _replay_query_path(ts, orc, pcs.fri, res, log_n + b, idx, rch=och.clone())
+
+
 @pytest.mark.parametrize("log_len,log_blowup", [(18, 1), (20, 3), (22, 4), (24, 2)])
 def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
     """FRI commit-phase sweep over BabyBear^4 codewords (config 5): the codeword is the LDE of a random
@@ -300,20 +374,7 @@ def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
         assert ref["ok"] and res.commits == ref["commits"] and np.array_equal(res.final_poly, ref["final_poly"])
         return
     # replay: betas from the commitments, then fold_row along the path of one index using opened layer rows
-    rch = orc.BfChallenger()
-    idx, folded = 987654321 % (1 << log_len), None
-    for r, (commit, pd) in enumerate(zip(res.commits, res.data)):
-        rch.observe_digest(commit)
-        beta = rch.sample_ef()
-        pair = idx >> 1
-        rows, path = cfg.mmcs.open_batch(pair, pd)
-        cfg.mmcs.verify_batch([1 << (log_len - 1 - r)], rows, pair, path, commit)
-        e0, e1 = rows[0][:4], rows[0][4:]
-        if folded is not None:
-            assert np.array_equal(folded, e1 if idx & 1 else e0)
-        folded = orc.fold_row_ef(pair, log_len - 1 - r, beta, e0, e1)
-        idx = pair
-    assert np.array_equal(folded, res.final_poly)
+    _replay_query_path(ts, orc, cfg, res, log_len, 987654321 % (1 << log_len))
 
 
 def test_pcs_open_verify(ts, ctx, orc):
