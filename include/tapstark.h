@@ -110,6 +110,19 @@ int ts_lde_batch(ts_ctx *ctx, const ts_matrix *evals, unsigned added_bits, ts_ma
 int ts_coset_lde_batch_host(ts_ctx *ctx, const uint32_t *evals_host, size_t rows, size_t width,
                             unsigned added_bits, uint32_t shift_monty, int natural_order, uint32_t *out_host);
 
+/* Host-buffer forms of the plain trait methods (dft_batch / idft_batch / coset_dft_batch of
+ * p3_dft::TwoAdicSubgroupDft; natural order in, natural order out; fri/src/fold_even_odd.rs:75-81 calls `dft`):
+ * H2D, transform, D2H inside the call.  shift_monty is used by TS_COSET_DFT only. */
+#define TS_DFT 0
+#define TS_IDFT 1
+#define TS_COSET_DFT 2
+int ts_dft_batch_host(ts_ctx *ctx, int kind, const uint32_t *mat_host, size_t rows, size_t width, uint32_t shift_monty,
+                      uint32_t *out_host);
+/* Page-lock / unlock a caller-owned host buffer (a Rust Vec<BabyBear> the prover keeps for the whole proof): the *_host
+ * entry points then copy it at the PCIe rate instead of the driver's pageable staging rate.  Optional. */
+int ts_host_register(ts_ctx *ctx, const void *host, size_t bytes);
+int ts_host_unregister(ts_ctx *ctx, const void *host);
+
 /* ---------------------------------------------------------------- basic::mmcs::bf_mmcs::BFMmcs<T>
  * (basic/src/mmcs/bf_mmcs.rs:17-68).  Blake3 row hash + 2-to-1 Blake3 tree over device-resident matrices.
  *   TS_LAYOUT_P3_INJECT : [MEM] p3-merkle-tree FieldMerkleTreeMmcs<.., SerializingHasher32<Blake3>,
@@ -194,6 +207,29 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *ctx, const ts_tree *t, size_t idx, 
  * TwoAdicFriPcs::open (`mat.dot_ext_powers(alpha)`, two_adic_pcs.rs:375).  alpha Montgomery. */
 int ts_dot_ext_powers(ts_ctx *ctx, const ts_matrix *m, const uint32_t alpha_monty[4], ts_matrix **out);
 
+
+/* Pcs::open (basic/src/bf_pcs.rs:61-74) = TwoAdicFriPcs::open (fri/src/two_adic_pcs.rs:260-419) followed by bf_prove
+ * (fri/src/prover.rs:19-90), whole, on the device-resident commitments -- what a Rust `impl Pcs for GpuTwoAdicFriPcs`
+ * calls; no host language has to re-implement the orchestration.
+ *   rounds[r]        prover data of the r-th ts_pcs_commit being opened
+ *   n_points[]       for every matrix of every round (round-major, matrices in commit order) its number of points
+ *   points_monty     4 u32 (Montgomery BabyBear^4) per point, in the same order
+ *   chal             the caller's challenger: sampled (alpha, betas, query indices) and observed (layer roots,
+ *                    proof-of-work witness) exactly as the reference does, so the caller's transcript continues
+ * Output: *out_bytes (free with ts_bytes_free) holds the postcard encoding (serde; the format the reference's own
+ * commented-out test uses, uni-stark/tests/mul_air.rs:133) of the pair `(OpenedValues, FriProof)`:
+ *   OpenedValues = Vec<Vec<Vec<Vec<Challenge>>>>                 round, matrix, point, column  (two_adic_pcs.rs:325-386)
+ *   FriProof { commit_phase_commits: Vec<[u8;32]>, query_proofs: Vec<BfQueryProof>, final_poly, pow_witness }
+ *   BfQueryProof { input_proof: Vec<BatchOpening { opened_values: Vec<Vec<Val>>, opening_proof: Vec<[u8;32]> }>,
+ *                  commit_phase_openings: Vec<(Vec<Vec<Challenge>>, Vec<[u8;32]>)> }             (fri/src/proof.rs:13-33)
+ * with unsigned integers and lengths as LEB128 varints, BabyBear as its canonical u32 ([MEM] p3-baby-bear's Serialize;
+ * parity unpinned -- no serialized vector exists in the reference), BabyBear^4 as 4 of them, digests as 32 raw bytes.
+ * The Merkle opening proof (sibling digests, leaf level first) stands where the reference has its Taproot
+ * CommitedProof. */
+int ts_pcs_open(ts_ctx *ctx, const ts_tree *const *rounds, size_t n_rounds, const size_t *n_points,
+                const uint32_t *points_monty, unsigned log_blowup, unsigned num_queries, unsigned proof_of_work_bits,
+                ts_challenger *chal, uint8_t **out_bytes, size_t *out_len);
+void ts_bytes_free(uint8_t *bytes);
 
 /* ---------------------------------------------------------------- quotient values (f3)
  * quotient_values of uni_stark::prove (uni-stark/src/prover.rs:122-194) on the device-resident trace LDE:

@@ -125,6 +125,11 @@ _SIGNATURES = {
     "ts_quotient_values": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
+    "ts_pcs_open": (C.c_int, [_vp, _vpp, C.c_size_t, _szp, _vp, C.c_uint, C.c_uint, C.c_uint, _vp, _vpp, _szp]),
+    "ts_bytes_free": (None, [_vp]),
+    "ts_dft_batch_host": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.c_size_t, C.c_uint32, _vp]),
+    "ts_host_register": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "ts_host_unregister": (C.c_int, [_vp, _vp]),
 }
 ABI_SYMBOLS = sorted(_SIGNATURES)
 
@@ -789,3 +794,31 @@ def _pcs_open(self, rounds, challenger: BfChallenger):
 
 
 TwoAdicFriPcs.open = _pcs_open
+
+
+def _pcs_open_bytes(self, rounds, challenger: BfChallenger) -> bytes:
+    """Pcs::open through ONE C-ABI call (ts_pcs_open): same arguments as `open`, returns the postcard bytes of
+    `(OpenedValues, FriProof)` -- decode with proofio.decode_opening."""
+    ctx, L = self.ctx, self.ctx._L
+    k = len(rounds)
+    trees = (C.c_void_p * k)(*[data._h for data, _ in rounds])
+    counts, pts = [], []
+    for data, points in rounds:
+        mats = self.mmcs.get_matrices(data)
+        if len(points) != len(mats):
+            raise TapStarkError("open: one point list per committed matrix")
+        for p_ in points:
+            counts.append(len(p_))
+            pts += [[int(x) for x in z] for z in p_]
+    n_points = (C.c_size_t * max(len(counts), 1))(*counts)
+    pm = to_monty(np.array(pts, dtype=np.uint32).reshape(-1)) if pts else np.zeros(4, dtype=np.uint32)
+    out, n = C.c_void_p(), C.c_size_t()
+    ctx.check(L.ts_pcs_open(ctx._h, trees, k, n_points, _ptr(pm), self.fri.log_blowup, self.fri.num_queries,
+                            self.fri.proof_of_work_bits, challenger._h, C.byref(out), C.byref(n)), "pcs_open")
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.ts_bytes_free(out)
+
+
+TwoAdicFriPcs.open_bytes = _pcs_open_bytes

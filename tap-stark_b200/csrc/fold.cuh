@@ -42,7 +42,14 @@ struct ChunkDeltas {
 __global__ void __launch_bounds__(FOLD_T) fold_ext_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
                                                           const uint4 *__restrict__ addend, int log_h, size_t first,
                                                           size_t h_local, ef::E4 half_beta, InvRootPows rp,
-                                                          ChunkDeltas dl, const uint32_t *__restrict__ tlo) {
+                                                          ChunkDeltas dl, const uint32_t *__restrict__ tlo,
+                                                          const uint32_t *__restrict__ half_beta_dev) {
+    // half_beta_dev != nullptr: beta/2 (4 Montgomery words) was left in device memory by the sponge step of this round
+    // (fri_tail.cuh: sponge_step_kernel), so no host round trip separates the layer's commitment from its fold
+    if (half_beta_dev) {
+        TS_UNROLL
+        for (int i = 0; i < 4; i++) half_beta.c[i] = half_beta_dev[i];
+    }
     const ef::E4Const hb = ef::prepare(half_beta);
     const size_t h = h_local;
     size_t c0 = 0, c1 = 1;

@@ -25,6 +25,7 @@ struct Params {
     uint32_t *layers[MAX_ROUNDS];    // layers[r]: output of round r (2^(log_len0 - r - 1) x 4) = leaves of round r + 1
     uint32_t *digests[MAX_ROUNDS];   // digests[r]: all tree layers of round r, leaves first (2 h_r - 1 nodes x 8 words)
     uint32_t prev_h[8];              // sponge state[8..16] on entry
+    const uint32_t *prev_h_dev;      // != nullptr: read it from device memory instead (left by sponge_step_kernel)
     uint32_t inv_gen[MAX_LOG_LEN + 2];  // two_adic_generator(b)^-1, Montgomery
     uint32_t *roots_out;             // rounds x 8 words
 };
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(NT) fri_tail_kernel(Params p) {
     TS_DYN_SMEM(uint32_t, sm);  // 12 words: sponge squeeze, beta / 2
     uint32_t *s_h = sm, *s_beta_half = sm + 8;
     const int tid = threadIdx.x;
-    if (tid < 8) s_h[tid] = p.prev_h[tid];
+    if (tid < 8) s_h[tid] = p.prev_h_dev ? p.prev_h_dev[tid] : p.prev_h[tid];
     __syncthreads();
     const uint32_t *cur = p.layer0;
     for (int r = 0; r < p.rounds; r++) {
@@ -109,6 +110,37 @@ __global__ void __launch_bounds__(NT) fri_tail_kernel(Params p) {
         }
         __syncthreads();
         cur = out;
+    }
+}
+
+// One commit-phase round's Fiat-Shamir step on the device (same sponge identity as above): combines the n_sub sub-roots of
+// a row-sharded layer (n_sub = 1: the root itself) into the layer root with the top log2(n_sub) tree levels, then
+// h = Blake3(root || h_prev), beta = (h[7], h[6], h[5], h[4]) mod p.  Leaves the root for the host's replay, the new h for
+// the next round and beta/2 (Montgomery) for this round's fold kernel -- nothing returns to the host between rounds.
+__global__ void sponge_step_kernel(const uint32_t *sub_roots, int n_sub, uint32_t *h_state, uint32_t *root_out,
+                                   uint32_t *half_beta_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t lvl[32][8];
+    for (int i = 0; i < n_sub; i++)
+        for (int k = 0; k < 8; k++) lvl[i][k] = sub_roots[i * 8 + k];
+    for (int w = n_sub; w > 1; w >>= 1)
+        for (int i = 0; i < w / 2; i++) {
+            uint32_t o[8];
+            b3::compress_pair(lvl[2 * i], lvl[2 * i + 1], b3::CHUNK_START | b3::CHUNK_END | b3::ROOT, o);
+            for (int k = 0; k < 8; k++) lvl[i][k] = o[k];
+        }
+    uint32_t hp[8], hn[8];
+    for (int k = 0; k < 8; k++) {
+        hp[k] = h_state[k];
+        root_out[k] = lvl[0][k];
+    }
+    b3::compress_pair(lvl[0], hp, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT, hn);
+    for (int k = 0; k < 8; k++) h_state[k] = hn[k];
+    for (int k = 0; k < 4; k++) {
+        uint32_t v = hn[7 - k];
+        v = v >= bb::P ? v - bb::P : v;
+        v = v >= bb::P ? v - bb::P : v;
+        half_beta_out[k] = bb::mmul(bb::to_monty(v), bb::MONTY_HALF);
     }
 }
 

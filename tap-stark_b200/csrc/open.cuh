@@ -127,4 +127,18 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const uint4 *__restric
     }
 }
 
+// Query-phase gather: segment s copies n_words[s] words from src[s] to dst + dst_off[s].  One launch packs the opened rows
+// and authentication paths of EVERY query of a tree into one buffer, which is read back with a single copy (round 1
+// issued one 32-byte device-to-host copy per tree level and per row: hundreds to thousands per proof).
+struct GatherSeg {
+    const uint32_t *src;
+    uint32_t dst_off, n_words;
+};
+__global__ void gather_segments_kernel(const GatherSeg *segs, uint32_t n_segs, uint32_t *dst) {
+    for (uint32_t s = blockIdx.x; s < n_segs; s += gridDim.x) {
+        const GatherSeg g = segs[s];
+        for (uint32_t i = threadIdx.x; i < g.n_words; i += blockDim.x) dst[g.dst_off + i] = g.src[i];
+    }
+}
+
 }  // namespace opn

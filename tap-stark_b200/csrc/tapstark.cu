@@ -6,6 +6,9 @@
 #include "../../include/tapstark.h"
 
 #include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <cstring>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -1144,11 +1147,13 @@ void h_ef_mul(const uint32_t a[4], const uint32_t b[4], uint32_t o[4]) {
     for (int i = 0; i < 4; i++) o[i] = i < 3 ? (uint32_t)((r[i] + 11ull * r[i + 4]) % bb::P) : r[i];
 }
 
+// beta_canon == nullptr: beta/2 is read from half_beta_dev (device, Montgomery) by the kernel
 int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t *addend, int log_h,
-                    const uint32_t beta_canon[4], size_t first = 0, size_t h_local = 0) {
+                    const uint32_t beta_canon[4], size_t first = 0, size_t h_local = 0, const uint32_t *half_beta_dev = nullptr) {
     const uint32_t half = bb::cinv(2);
     ef::E4 hb;
-    for (int i = 0; i < 4; i++) hb.c[i] = h_to_monty(bb::cmul(beta_canon[i], half));
+    for (int i = 0; i < 4; i++) hb.c[i] = beta_canon ? h_to_monty(bb::cmul(beta_canon[i], half)) : 0;
+    if (!beta_canon && !half_beta_dev) TS_FAIL(c, TS_ERR_ARG, "fold: no beta");
     const uint32_t g_inv = bb::cinv(bb::two_adic_generator(log_h + 1));
     fold::InvRootPows rp;
     uint32_t r = g_inv;
@@ -1176,7 +1181,7 @@ int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t
     KScope ks(c, TS_K_FOLD);
     auto kfn = fold::fold_ext_kernel;
     TS_LAUNCH(kfn, blocks, fold::FOLD_T, 0, c->stream, (const uint4 *)in, (uint4 *)out, (const uint4 *)addend, log_h,
-              first, h, hb, rp, dl, (const uint32_t *)c->fold_tlo);
+              first, h, hb, rp, dl, (const uint32_t *)c->fold_tlo, beta_canon ? (const uint32_t *)nullptr : half_beta_dev);
     return check_launch(c, "fold_ext_kernel");
 }
 
@@ -1484,6 +1489,34 @@ int ts_idft_batch(ts_ctx *c, const ts_matrix *evals, ts_matrix **out) {
 int ts_coset_dft_batch(ts_ctx *c, const ts_matrix *coeffs, uint32_t shift_monty, ts_matrix **out) {
     return plain_transform(c, false, coeffs, true, shift_monty, out);
 }
+int ts_dft_batch_host(ts_ctx *c, int kind, const uint32_t *mat_host, size_t rows, size_t width, uint32_t shift_monty,
+                      uint32_t *out_host) {
+    if (!c || !mat_host || !out_host || kind < TS_DFT || kind > TS_COSET_DFT) TS_FAIL(c, TS_ERR_ARG, "dft_batch_host: bad argument");
+    ts_matrix *in = nullptr, *out = nullptr;
+    TS_TRY(ts_matrix_from_host(c, mat_host, rows, width, &in));
+    int rc = plain_transform(c, kind == TS_IDFT, in, kind == TS_COSET_DFT, shift_monty, &out);
+    ts_matrix_free(in);
+    if (rc != TS_OK) return rc;
+    rc = ts_matrix_download(c, out, 0, rows, out_host);
+    ts_matrix_free(out);
+    return rc;
+}
+int ts_host_register(ts_ctx *c, const void *host, size_t bytes) {
+#ifndef TS_EMULATE
+    TS_CUDA(c, cudaHostRegister(const_cast<void *>(host), bytes, cudaHostRegisterDefault));
+#else
+    (void)host, (void)bytes;
+#endif
+    return TS_OK;
+}
+int ts_host_unregister(ts_ctx *c, const void *host) {
+#ifndef TS_EMULATE
+    TS_CUDA(c, cudaHostUnregister(const_cast<void *>(host)));
+#else
+    (void)host;
+#endif
+    return TS_OK;
+}
 int ts_coset_lde_batch_host(ts_ctx *c, const uint32_t *evals_host, size_t rows, size_t width, unsigned added_bits,
                             uint32_t shift_monty, int natural_order, uint32_t *out_host) {
     ts_matrix *in = nullptr, *o = nullptr;
@@ -1676,7 +1709,8 @@ int ts_fri_fold_ext_host(ts_ctx *c, const uint32_t *in_host, size_t h, const uin
 // layer; when it is owned it becomes the leaf matrix of the first tail tree (or is released), otherwise it is only read.
 // Appends to commits / trees from index `round` on and advances it; the final layer lands in c->tail_final.
 static int fri_tail(ts_ctx *c, ts_challenger *chal, uint32_t *cur, bool cur_owned, size_t len, unsigned log_blowup,
-                    uint8_t *commits, ts_tree **trees, size_t &round) {
+                    uint8_t *commits, ts_tree **trees, size_t &round, const uint32_t *prev_h_dev = nullptr,
+                    const std::function<void()> *before_replay = nullptr) {
     const int log_len = log2_strict(len);
     const int rounds = log_len - (int)log_blowup;
     ftail::Params p;
@@ -1684,6 +1718,7 @@ static int fri_tail(ts_ctx *c, ts_challenger *chal, uint32_t *cur, bool cur_owne
     p.log_len0 = log_len;
     p.rounds = rounds;
     memcpy(p.prev_h, &chal->state[8][0], 32);
+    p.prev_h_dev = prev_h_dev;
     for (int b = 0; b < ftail::MAX_LOG_LEN + 2; b++) p.inv_gen[b] = h_to_monty(bb::cinv(bb::two_adic_generator(b)));
     std::vector<ts_tree *> tt((size_t)rounds, nullptr);
     uint32_t *roots_dev = nullptr;
@@ -1746,6 +1781,7 @@ static int fri_tail(ts_ctx *c, ts_challenger *chal, uint32_t *cur, bool cur_owne
     }
     if (layer_in) pool_release(c, layer_in);  // the final layer is owned by no tree
     if (roots_dev) pool_release(c, roots_dev);
+    if (rc == TS_OK && before_replay) (*before_replay)();  // the chained rounds before the tail are replayed first
     if (rc == TS_OK) {
         for (int r = 0; r < rounds; r++) {  // replay the sponge on the host: it stays the source of truth
             const uint8_t *root = reinterpret_cast<const uint8_t *>(host.data() + (size_t)r * 8);
@@ -1795,11 +1831,51 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         cur = cl;
         cur_owned = true;
     }
+    // Chained rounds: while whole digests are all the challenger observes, its state after a round is (root, previous
+    // squeeze), so the sponge step runs on the device (fri_tail.cuh: sponge_step_kernel) and leaves beta/2 where the fold
+    // kernel reads it: no round waits for a 32-byte read-back and a host hash.  The roots come back ONCE, with the final
+    // layer, and the host challenger replays them (it stays the source of truth for grinding and the query phase).
+    const bool chain = chal->in_buf.empty() && getenv("TS_NO_FRI_CHAIN") == nullptr;
+    const size_t max_rounds = (size_t)std::max(log2_strict(len) - (int)log_blowup, 0);
+    uint32_t *d_chain = nullptr;  // [0,8): h  [8,12): beta/2  [12, 12 + 8*max_rounds): roots
+    std::vector<uint32_t> chain_roots;
+    size_t chain_pending = 0, chain_first = 0;
+    if (chain && max_rounds > 0) {
+        TS_CUDA(c, pool_alloc(c, (void **)&d_chain, (12 + 8 * max_rounds) * 4));
+        uint32_t h0[8];
+        memcpy(h0, &chal->state[8][0], 32);
+        cudaError_t e = cudaMemcpyAsync(d_chain, h0, 32, cudaMemcpyHostToDevice, c->stream);  // pageable source: staged before return
+        if (e != cudaSuccess) {
+            pool_release(c, d_chain);
+            TS_FAIL(c, TS_ERR_CUDA, std::string("chain init: ") + cudaGetErrorString(e));
+        }
+        chain_roots.resize(8 * max_rounds);
+    }
+    auto replay_chain = [&]() {  // after a synchronisation: the host challenger catches up with the chained rounds
+        for (size_t k = 0; k < chain_pending; k++) {
+            const uint8_t *root = reinterpret_cast<const uint8_t *>(chain_roots.data() + 8 * k);
+            memcpy(commits + 32 * (chain_first + k), root, 32);
+            ts_challenger_observe_digest(chal, root);  // prover.rs:114
+            uint32_t beta[4];
+            ts_challenger_sample_ext(chal, beta);      // prover.rs:116
+        }
+        chain_pending = 0;
+    };
     while (len > blowup) {
         if (len <= ((size_t)1 << ftail::MAX_LOG_LEN) && next_in >= n_inputs && chal->in_buf.empty() &&
             getenv("TS_NO_FRI_TAIL") == nullptr) {
             // every remaining round in one launch, sponge included (fri_tail.cuh)
-            rc = fri_tail(c, chal, cur, cur_owned, len, log_blowup, commits, trees, round);
+            const std::function<void()> hook = replay_chain;
+            if (chain_pending) {
+                cudaError_t e = cudaMemcpyAsync(chain_roots.data(), d_chain + 12 + 8 * chain_first, chain_pending * 32,
+                                                cudaMemcpyDeviceToHost, c->stream);
+                if (e != cudaSuccess) {
+                    c->err = std::string("chain roots download: ") + cudaGetErrorString(e);
+                    rc = TS_ERR_CUDA;
+                    break;
+                }
+            }
+            rc = fri_tail(c, chal, cur, cur_owned, len, log_blowup, commits, trees, round, d_chain, &hook);
             cur = nullptr;  // consumed: owned by the first tail tree or released
             cur_owned = false;
             if (rc == TS_OK) {
@@ -1812,6 +1888,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
                         rc = TS_ERR_NOT_CONSTANT;
                     }
             }
+            if (d_chain) pool_release(c, d_chain);
             if (rounds_out) *rounds_out = round;
             return rc;
         }
@@ -1820,26 +1897,37 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         ts_matrix *leaves = new ts_matrix{c, cur, h, 8, cur_owned};
         ts_tree *tree = nullptr;
         uint8_t root[32];
-        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, root, &tree, true);  // prover.rs:113
+        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, d_chain ? nullptr : root, &tree, true);  // prover.rs:113
         if (rc != TS_OK) {
             ts_matrix_free(leaves);
             cur = nullptr;
             break;
         }
         // the tree now owns `leaves` (and the layer buffer when it was ours)
-        memcpy(commits + 32 * round, root, 32);
-        ts_challenger_observe_digest(chal, root);  // prover.rs:114
         uint32_t beta[4];
-        ts_challenger_sample_ext(chal, beta);  // prover.rs:116
+        if (d_chain) {
+            if (chain_pending == 0) chain_first = round;
+            KScope ks(c, TS_K_TREE);
+            auto kfn = ftail::sponge_step_kernel;
+            TS_LAUNCH(kfn, 1, 32, 0, c->stream, (const uint32_t *)(tree->digests + tree->layer_off[tree->lmax] * 8), 1, d_chain,
+                      d_chain + 12 + 8 * round, d_chain + 8);
+            rc = check_launch(c, "sponge_step_kernel");
+            chain_pending++;
+        } else {
+            memcpy(commits + 32 * round, root, 32);
+            ts_challenger_observe_digest(chal, root);  // prover.rs:114
+            ts_challenger_sample_ext(chal, beta);      // prover.rs:116
+        }
         uint32_t *nf = nullptr;
-        cudaError_t e = pool_alloc(c, (void **)&nf, h * 16);
-        if (e != cudaSuccess) {
+        cudaError_t e = rc == TS_OK ? pool_alloc(c, (void **)&nf, h * 16) : cudaSuccess;
+        if (rc != TS_OK) {
+        } else if (e != cudaSuccess) {
             c->err = std::string("cudaMalloc folded: ") + cudaGetErrorString(e);
             rc = TS_ERR_CUDA;
         } else {
             const uint32_t *addend = nullptr;
             if (next_in < n_inputs && inputs[next_in]->rows == h) addend = inputs[next_in++]->d;  // prover.rs:124-126
-            rc = fold_ext_launch(c, cur, nf, addend, log2_strict(h), beta);  // prover.rs:119
+            rc = fold_ext_launch(c, cur, nf, addend, log2_strict(h), d_chain ? nullptr : beta, 0, 0, d_chain ? d_chain + 8 : nullptr);  // prover.rs:119
         }
         cur = nullptr;
         cur_owned = false;
@@ -1857,11 +1945,14 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
     if (rc == TS_OK) {
         std::vector<uint32_t> tail(len * 4);
         cudaError_t e = cudaMemcpyAsync(tail.data(), cur, len * 16, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && chain_pending)
+            e = cudaMemcpyAsync(chain_roots.data(), d_chain + 12 + 8 * chain_first, chain_pending * 32, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) {
             c->err = std::string("final layer download: ") + cudaGetErrorString(e);
             rc = TS_ERR_CUDA;
         } else {
+            replay_chain();
             for (int i = 0; i < 4; i++) final_poly[i] = h_from_monty(tail[i]);
             for (size_t i = 1; i < len; i++)
                 if (memcmp(&tail[4 * i], &tail[0], 16) != 0) {  // prover.rs:130-134
@@ -1870,6 +1961,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
                 }
         }
     }
+    if (d_chain) pool_release(c, d_chain);
     if (cur_owned && cur) pool_release(c, cur);
     if (rounds_out) *rounds_out = round;
     return rc;
@@ -2355,6 +2447,277 @@ int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, si
     for (int i = 0; i < 4; i++) beta[i] = h_from_monty(beta_monty[i]);
     return fold_ext_launch(c, in_dev, out_dev, addend_dev, lh, beta, first, h_local);
 }
+
+// ---------------------------------------------------------------- Pcs::open + bf_prove behind the ABI, proof bytes
+namespace {
+// rows (concatenated over the tree's matrices) and paths of many indices of one tree: one gather launch, one read-back
+int open_many(ts_ctx *c, const ts_tree *t, const std::vector<size_t> &idx, std::vector<uint32_t> &rows, std::vector<uint8_t> &paths,
+              size_t *row_words_out) {
+    size_t row_words = 0;
+    for (const ts_matrix *m : t->mats) row_words += m->width;
+    *row_words_out = row_words;
+    const size_t q = idx.size(), per = row_words + 8 * (size_t)t->lmax;
+    rows.assign(q * row_words, 0);
+    paths.assign(q * 32 * (size_t)t->lmax, 0);
+    if (q == 0 || per == 0) return TS_OK;
+    std::vector<opn::GatherSeg> segs;
+    for (size_t k = 0; k < q; k++) {
+        if (idx[k] >= t->hmax) TS_FAIL(c, TS_ERR_ARG, "open: index out of range");
+        size_t o = k * per;
+        for (const ts_matrix *m : t->mats) {
+            const size_t row = idx[k] >> (t->lmax - (unsigned)log2_strict(m->rows));
+            segs.push_back({m->d + row * m->width, (uint32_t)o, (uint32_t)m->width});
+            o += m->width;
+        }
+        for (unsigned l = 0; l < t->lmax; l++) {
+            const size_t node = (idx[k] >> l) ^ 1;
+            segs.push_back({t->digests + (t->layer_off[l] + node) * 8, (uint32_t)o, 8u});
+            o += 8;
+        }
+    }
+    opn::GatherSeg *dsegs = nullptr;
+    uint32_t *dbuf = nullptr;
+    TS_CUDA(c, pool_alloc(c, (void **)&dsegs, segs.size() * sizeof(opn::GatherSeg)));
+    cudaError_t e = pool_alloc(c, (void **)&dbuf, q * per * 4);
+    if (e != cudaSuccess) {
+        pool_release(c, dsegs);
+        TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    std::vector<uint32_t> host(q * per);
+    int rc = TS_OK;
+    e = cudaMemcpyAsync(dsegs, segs.data(), segs.size() * sizeof(opn::GatherSeg), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = opn::gather_segments_kernel;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>(segs.size(), 4096), 64, 0, c->stream, (const opn::GatherSeg *)dsegs,
+                  (uint32_t)segs.size(), dbuf);
+        rc = check_launch(c, "gather_segments_kernel");
+    }
+    if (e == cudaSuccess && rc == TS_OK) e = cudaMemcpyAsync(host.data(), dbuf, q * per * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && rc == TS_OK) e = cudaStreamSynchronize(c->stream);
+    pool_release(c, dsegs);
+    pool_release(c, dbuf);
+    if (e != cudaSuccess) TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
+    if (rc != TS_OK) return rc;
+    for (size_t k = 0; k < q; k++) {
+        memcpy(rows.data() + k * row_words, host.data() + k * per, row_words * 4);
+        memcpy(paths.data() + k * 32 * (size_t)t->lmax, host.data() + k * per + row_words, 32 * (size_t)t->lmax);
+    }
+    return TS_OK;
+}
+
+// postcard (serde) wire format: unsigned integers as LEB128 varints, Vec<T> = varint length + elements, fixed arrays and
+// tuples/structs = elements in order, u8 = one raw byte.  BabyBear = its canonical u32 ([MEM] p3-baby-bear Serialize).
+struct Postcard {
+    std::vector<uint8_t> b;
+    void varint(uint64_t v) {
+        while (v >= 0x80) {
+            b.push_back((uint8_t)(v | 0x80));
+            v >>= 7;
+        }
+        b.push_back((uint8_t)v);
+    }
+    void len(size_t n) { varint(n); }
+    void bb_monty(uint32_t m) { varint(h_from_monty(m)); }
+    void bb_canon(uint32_t v) { varint(v); }
+    void digest(const uint8_t *d) { b.insert(b.end(), d, d + 32); }
+    void path(const uint8_t *p, size_t depth) {  // Vec<[u8; 32]>
+        len(depth);
+        b.insert(b.end(), p, p + 32 * depth);
+    }
+};
+void h_ef_pow(const uint32_t a[4], uint64_t e, uint32_t o[4]) {
+    uint32_t r[4] = {1, 0, 0, 0}, base[4], t[4];
+    memcpy(base, a, 16);
+    while (e) {
+        if (e & 1) {
+            h_ef_mul(r, base, t);
+            memcpy(r, t, 16);
+        }
+        h_ef_mul(base, base, t);
+        memcpy(base, t, 16);
+        e >>= 1;
+    }
+    memcpy(o, r, 16);
+}
+}  // namespace
+
+int ts_pcs_open(ts_ctx *c, const ts_tree *const *rounds, size_t n_rounds, const size_t *n_points, const uint32_t *points_monty,
+                unsigned log_blowup, unsigned num_queries, unsigned pow_bits, ts_challenger *chal, uint8_t **out_bytes,
+                size_t *out_len) {
+    if (!c || !rounds || !n_rounds || !n_points || !chal || !out_bytes || !out_len) TS_FAIL(c, TS_ERR_ARG, "pcs_open: null argument");
+    *out_bytes = nullptr;
+    *out_len = 0;
+    uint32_t alpha[4], alpha_m[4];  // :312  alpha = challenger.sample()
+    ts_challenger_sample_ext(chal, alpha);
+    for (int i = 0; i < 4; i++) alpha_m[i] = h_to_monty(alpha[i]);
+    // (round, matrix) -> first point index
+    struct MatRef { const ts_matrix *m; size_t first_point, n_points; };
+    std::vector<std::vector<MatRef>> mats(n_rounds);
+    size_t pt = 0, mi = 0;
+    unsigned log_global_max_height = 0;
+    for (size_t r = 0; r < n_rounds; r++) {
+        if (!rounds[r]) TS_FAIL(c, TS_ERR_ARG, "pcs_open: null round");
+        for (const ts_matrix *m : rounds[r]->mats) {
+            const int lh = log2_strict(m->rows);
+            if (lh < (int)log_blowup) TS_FAIL(c, TS_ERR_ARG, "pcs_open: matrix shorter than the blowup");
+            mats[r].push_back({m, pt, n_points[mi]});
+            pt += n_points[mi++];
+            log_global_max_height = std::max(log_global_max_height, (unsigned)lh);
+        }
+    }
+    if (pt && !points_monty) TS_FAIL(c, TS_ERR_ARG, "pcs_open: null points");
+    // compute_inverse_denominators (:677-720): per unique point, for the largest height it is opened at
+    std::map<std::array<uint32_t, 4>, unsigned> max_lh;
+    auto key_of = [&](size_t p) { return std::array<uint32_t, 4>{points_monty[4 * p], points_monty[4 * p + 1], points_monty[4 * p + 2], points_monty[4 * p + 3]}; };
+    for (auto &rm : mats)
+        for (auto &mr : rm)
+            for (size_t k = 0; k < mr.n_points; k++) {
+                auto key = key_of(mr.first_point + k);
+                max_lh[key] = std::max(max_lh.count(key) ? max_lh[key] : 0u, (unsigned)log2_strict(mr.m->rows));
+            }
+    std::map<std::array<uint32_t, 4>, ts_matrix *> inv;
+    std::map<unsigned, ts_matrix *> reduced;
+    std::map<unsigned, size_t> num_reduced;
+    std::vector<ts_tree *> fri_trees;
+    auto cleanup = [&]() {
+        for (auto &kv : inv) ts_matrix_free(kv.second);
+        for (auto &kv : reduced) ts_matrix_free(kv.second);
+        for (ts_tree *t : fri_trees) ts_tree_free(t);
+    };
+#define PO_TRY(expr)           \
+    do {                       \
+        int rc__ = (expr);     \
+        if (rc__ != TS_OK) {   \
+            cleanup();         \
+            return rc__;       \
+        }                      \
+    } while (0)
+    for (auto &kv : max_lh) {
+        ts_matrix *d = nullptr;
+        PO_TRY(ts_inv_denoms(c, kv.second, kv.first.data(), &d));
+        inv[kv.first] = d;
+    }
+    Postcard pc;
+    // all_opened_values: Vec (round) < Vec (matrix) < Vec (point) < Vec<Challenge> > > >
+    pc.len(n_rounds);
+    for (size_t r = 0; r < n_rounds; r++) {
+        pc.len(mats[r].size());
+        for (auto &mr : mats[r]) {
+            const ts_matrix *m = mr.m;
+            const unsigned lh = (unsigned)log2_strict(m->rows);
+            if (!reduced.count(lh)) {
+                ts_matrix *ro = nullptr;
+                PO_TRY(new_matrix(c, m->rows, 4, &ro));
+                reduced[lh] = ro;
+                num_reduced[lh] = 0;
+                PO_TRY(ts_matrix_zero(c, ro));
+            }
+            ts_matrix *dot = nullptr;  // sum_i alpha^i p_i[X], shared by all points of this matrix (:375)
+            if (mr.n_points) PO_TRY(ts_dot_ext_powers(c, m, alpha_m, &dot));
+            pc.len(mr.n_points);
+            std::vector<uint32_t> ys(m->width * 4);
+            for (size_t k = 0; k < mr.n_points; k++) {
+                const uint32_t *zm = points_monty + 4 * (mr.first_point + k);
+                ts_matrix *idn = inv[key_of(mr.first_point + k)];
+                int rc = ts_interpolate_low_coset(c, m, m->rows >> log_blowup, zm, idn, ys.data());  // :358-369
+                uint32_t apo[4], rys[4] = {0, 0, 0, 0}, ap[4] = {1, 0, 0, 0}, apo_m[4], rys_m[4];
+                if (rc == TS_OK) {
+                    h_ef_pow(alpha, num_reduced[lh], apo);
+                    pc.len(m->width);
+                    for (size_t col = 0; col < m->width; col++) {  // dot_product(alpha.powers(), ys)
+                        uint32_t y[4], t[4];
+                        for (int i = 0; i < 4; i++) {
+                            y[i] = h_from_monty(ys[4 * col + i]);
+                            pc.bb_canon(y[i]);
+                        }
+                        h_ef_mul(ap, y, t);
+                        for (int i = 0; i < 4; i++) rys[i] = (uint32_t)(((uint64_t)rys[i] + t[i]) % bb::P);
+                        h_ef_mul(ap, alpha, t);
+                        memcpy(ap, t, 16);
+                    }
+                    for (int i = 0; i < 4; i++) apo_m[i] = h_to_monty(apo[i]), rys_m[i] = h_to_monty(rys[i]);
+                    rc = ts_reduce_opening_acc(c, dot, idn, apo_m, rys_m, reduced[lh]);  // :371-381
+                    num_reduced[lh] += m->width;
+                }
+                if (rc != TS_OK) {
+                    ts_matrix_free(dot);
+                    cleanup();
+                    return rc;
+                }
+            }
+            if (dot) ts_matrix_free(dot);
+        }
+    }
+    // fri_input: reduced openings sorted by height, descending (:389); bf_prove (fri/src/prover.rs:19-67)
+    std::vector<ts_matrix *> fri_in;
+    for (auto it = reduced.rbegin(); it != reduced.rend(); ++it) fri_in.push_back(it->second);
+    const size_t max_rounds = log_global_max_height > log_blowup ? log_global_max_height - log_blowup : 0;
+    std::vector<uint8_t> commits(32 * std::max<size_t>(max_rounds, 1));
+    fri_trees.assign(std::max<size_t>(max_rounds, 1), nullptr);
+    uint32_t final_poly[4];
+    size_t n_fri = 0;
+    {
+        int rc = ts_fri_commit_phase(c, fri_in.data(), fri_in.size(), log_blowup, chal, commits.data(), fri_trees.data(), final_poly, &n_fri);
+        PO_TRY(rc);
+        fri_trees.resize(n_fri);  // entries beyond the rounds actually run are null
+    }
+    uint32_t pow_witness = 0;
+    PO_TRY(ts_challenger_grind(chal, pow_bits, 1, &pow_witness));
+    std::vector<size_t> index(num_queries);
+    for (unsigned q = 0; q < num_queries; q++) index[q] = ts_challenger_sample_bits(chal, log_global_max_height, 1);
+    // query phase: per tree, every query's rows + path in one gather
+    struct Opened { std::vector<uint32_t> rows; std::vector<uint8_t> paths; size_t row_words; };
+    std::vector<Opened> in_open(n_rounds), fri_open(n_fri);
+    for (size_t r = 0; r < n_rounds; r++) {
+        std::vector<size_t> idx(num_queries);
+        for (unsigned q = 0; q < num_queries; q++) idx[q] = index[q] >> (log_global_max_height - rounds[r]->lmax);  // :399-413
+        PO_TRY(open_many(c, rounds[r], idx, in_open[r].rows, in_open[r].paths, &in_open[r].row_words));
+    }
+    for (size_t i = 0; i < n_fri; i++) {
+        std::vector<size_t> idx(num_queries);
+        for (unsigned q = 0; q < num_queries; q++) idx[q] = index[q] >> i >> 1;  // prover.rs:69-90
+        PO_TRY(open_many(c, fri_trees[i], idx, fri_open[i].rows, fri_open[i].paths, &fri_open[i].row_words));
+    }
+    // FriProof { commit_phase_commits, query_proofs, final_poly, pow_witness }  (fri/src/proof.rs:13-33)
+    pc.len(n_fri);
+    for (size_t i = 0; i < n_fri; i++) pc.digest(commits.data() + 32 * i);
+    pc.len(num_queries);
+    for (unsigned q = 0; q < num_queries; q++) {
+        pc.len(n_rounds);  // input_proof: Vec<BatchOpening { opened_values: Vec<Vec<Val>>, opening_proof }>
+        for (size_t r = 0; r < n_rounds; r++) {
+            const ts_tree *t = rounds[r];
+            pc.len(t->mats.size());
+            size_t o = q * in_open[r].row_words;
+            for (const ts_matrix *m : t->mats) {
+                pc.len(m->width);
+                for (size_t k = 0; k < m->width; k++) pc.bb_monty(in_open[r].rows[o + k]);
+                o += m->width;
+            }
+            pc.path(in_open[r].paths.data() + (size_t)q * 32 * t->lmax, t->lmax);
+        }
+        pc.len(n_fri);  // commit_phase_openings: Vec<(Vec<Vec<F>>, Proof)>
+        for (size_t i = 0; i < n_fri; i++) {
+            const ts_tree *t = fri_trees[i];
+            pc.len(1);
+            pc.len(2);
+            for (int k = 0; k < 8; k++) pc.bb_monty(fri_open[i].rows[q * fri_open[i].row_words + k]);
+            pc.path(fri_open[i].paths.data() + (size_t)q * 32 * t->lmax, t->lmax);
+        }
+    }
+    for (int i = 0; i < 4; i++) pc.bb_canon(final_poly[i]);
+    pc.bb_canon(pow_witness);
+    cleanup();
+#undef PO_TRY
+    uint8_t *buf = (uint8_t *)malloc(pc.b.size() ? pc.b.size() : 1);
+    if (!buf) TS_FAIL(c, TS_ERR_ARG, "pcs_open: out of host memory");
+    memcpy(buf, pc.b.data(), pc.b.size());
+    *out_bytes = buf;
+    *out_len = pc.b.size();
+    return TS_OK;
+}
+void ts_bytes_free(uint8_t *p) { free(p); }
+
 void ts_blake3_host(const uint8_t *in, size_t len, uint8_t out[32]) { hostb3::hash(in, len, out); }
 
 }  // extern "C"

@@ -10,7 +10,8 @@
 //   FriConfig                    fri::FriConfig                            fri/src/config.rs:10-22
 //   fold_even_odd                fri::fold_even_odd                        fri/src/fold_even_odd.rs:20-52
 //   bf_commit_phase              fri::prover::bf_commit_phase              fri/src/prover.rs:93-141
-//   TwoAdicFriPcs                impl Pcs for TwoAdicFriPcs (commit side)  fri/src/two_adic_pcs.rs:197-258
+//   TwoAdicFriPcs                impl Pcs for TwoAdicFriPcs: commit :227-258, open :260-419 (one ts_pcs_open call)
+//   FriProof / BfQueryProof / BatchOpening   fri/src/proof.rs:13-33, decoded from the postcard bytes of ts_pcs_open
 //
 // Header only; link with libtapstark_b200.so.  All compute is in the CUDA library.
 #pragma once
@@ -301,6 +302,104 @@ inline CommitPhaseResult bf_commit_phase(const FriConfig &config, const std::vec
     return res;
 }
 
+// ---- proof objects (fri/src/proof.rs:13-33; canonical u32 values, as serialised) -------------------------------------
+struct BatchOpening {
+    std::vector<std::vector<Val>> opened_values;  // canonical
+    BatchOpeningProof opening_proof;
+};
+struct CommitPhaseStep {
+    std::vector<std::vector<Challenge>> opened_rows;  // one matrix: [[e0, e1]], canonical
+    BatchOpeningProof opening_proof;
+};
+struct BfQueryProof {
+    std::vector<BatchOpening> input_proof;
+    std::vector<CommitPhaseStep> commit_phase_openings;
+};
+struct FriProof {
+    std::vector<Digest> commit_phase_commits;
+    std::vector<BfQueryProof> query_proofs;
+    Challenge final_poly;  // canonical
+    uint32_t pow_witness;
+};
+// all_opened_values[round][matrix][point][column], canonical BabyBear^4
+using OpenedValues = std::vector<std::vector<std::vector<std::vector<Challenge>>>>;
+
+// postcard reader (include/tapstark.h: ts_pcs_open documents the layout)
+class PostcardReader {
+public:
+    PostcardReader(const uint8_t *p, size_t n) : p_(p), n_(n) {}
+    uint64_t varint() {
+        uint64_t v = 0;
+        for (int s = 0;; s += 7) {
+            if (o_ >= n_ || s > 63) throw Panic("postcard: truncated varint");
+            const uint8_t x = p_[o_++];
+            v |= (uint64_t)(x & 0x7f) << s;
+            if (x < 0x80) return v;
+        }
+    }
+    Challenge ef() { return {(uint32_t)varint(), (uint32_t)varint(), (uint32_t)varint(), (uint32_t)varint()}; }
+    Digest digest() {
+        if (o_ + 32 > n_) throw Panic("postcard: truncated digest");
+        Digest d;
+        std::copy(p_ + o_, p_ + o_ + 32, d.begin());
+        o_ += 32;
+        return d;
+    }
+    BatchOpeningProof path() {
+        BatchOpeningProof pr;
+        pr.siblings.resize(varint());
+        for (auto &d : pr.siblings) d = digest();
+        return pr;
+    }
+    bool done() const { return o_ == n_; }
+
+private:
+    const uint8_t *p_;
+    size_t n_, o_ = 0;
+};
+inline std::pair<OpenedValues, FriProof> decode_opening(const std::vector<uint8_t> &bytes) {
+    PostcardReader r(bytes.data(), bytes.size());
+    OpenedValues ov(r.varint());
+    for (auto &rnd : ov) {
+        rnd.resize(r.varint());
+        for (auto &mat : rnd) {
+            mat.resize(r.varint());
+            for (auto &pt : mat) {
+                pt.resize(r.varint());
+                for (auto &y : pt) y = r.ef();
+            }
+        }
+    }
+    FriProof pr;
+    pr.commit_phase_commits.resize(r.varint());
+    for (auto &d : pr.commit_phase_commits) d = r.digest();
+    pr.query_proofs.resize(r.varint());
+    for (auto &q : pr.query_proofs) {
+        q.input_proof.resize(r.varint());
+        for (auto &bo : q.input_proof) {
+            bo.opened_values.resize(r.varint());
+            for (auto &row : bo.opened_values) {
+                row.resize(r.varint());
+                for (auto &v : row) v = (uint32_t)r.varint();
+            }
+            bo.opening_proof = r.path();
+        }
+        q.commit_phase_openings.resize(r.varint());
+        for (auto &st : q.commit_phase_openings) {
+            st.opened_rows.resize(r.varint());
+            for (auto &row : st.opened_rows) {
+                row.resize(r.varint());
+                for (auto &e : row) e = r.ef();
+            }
+            st.opening_proof = r.path();
+        }
+    }
+    pr.final_poly = r.ef();
+    pr.pow_witness = (uint32_t)r.varint();
+    if (!r.done()) throw Panic("postcard: trailing bytes after the opening proof");
+    return {std::move(ov), std::move(pr)};
+}
+
 struct TwoAdicMultiplicativeCoset {
     size_t log_n;
     Val shift;  // Montgomery
@@ -344,6 +443,35 @@ public:
         std::vector<Val> v(domain.size() * w);
         c.check(ts_pcs_get_evaluations_on_domain(c.raw(), pd.raw(), idx, domain.size(), v.data()), "get_evaluations_on_domain");
         return RowMajorMatrix<Val>(std::move(v), w);
+    }
+    // two_adic_pcs.rs:260-419 + fri/src/prover.rs:19-90.  rounds: (prover data, per matrix its opening points in Montgomery
+    // form).  The serialised `(OpenedValues, FriProof)` exactly as the library emits it:
+    std::vector<uint8_t> open_bytes(const std::vector<std::pair<const ProverData *, std::vector<std::vector<Challenge>>>> &rounds,
+                                    BfChallenger &challenger) const {
+        const Context &c = mmcs_->ctx();
+        std::vector<const ts_tree *> trees;
+        std::vector<size_t> counts;
+        std::vector<uint32_t> pts;
+        for (auto &r : rounds) {
+            if (r.second.size() != ts_tree_num_matrices(r.first->raw())) throw Panic("open: one point list per committed matrix");
+            trees.push_back(r.first->raw());
+            for (auto &per_mat : r.second) {
+                counts.push_back(per_mat.size());
+                for (auto &z : per_mat) pts.insert(pts.end(), z.begin(), z.end());
+            }
+        }
+        uint8_t *buf = nullptr;
+        size_t n = 0;
+        c.check(ts_pcs_open(c.raw(), trees.data(), trees.size(), counts.data(), pts.data(), (unsigned)fri_.log_blowup,
+                            (unsigned)fri_.num_queries, (unsigned)fri_.proof_of_work_bits, challenger.raw(), &buf, &n),
+                "pcs open");
+        std::vector<uint8_t> out(buf, buf + n);
+        ts_bytes_free(buf);
+        return out;
+    }
+    std::pair<OpenedValues, FriProof> open(const std::vector<std::pair<const ProverData *, std::vector<std::vector<Challenge>>>> &rounds,
+                                           BfChallenger &challenger) const {
+        return decode_opening(open_bytes(rounds, challenger));
     }
     const FriConfig &fri() const { return fri_; }
     const Blake3MerkleMmcs &mmcs() const { return *mmcs_; }

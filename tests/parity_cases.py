@@ -224,7 +224,17 @@ def check_pcs_open_verify(ts, ctx, orc, round_shapes, log_blowup, num_queries=6,
         pts_dev.append((data, per_mat))
         pts_ora.append(list(zip(ldes, per_mat)))
     och_v = och.clone()
+    ch_abi = ch.clone()
     opened, proof = pcs.open(pts_dev, ch)
+    # the same opening through the single C-ABI call (ts_pcs_open): its bytes are the oracle's postcard encoding of the
+    # host-orchestrated result, they decode to a proof the restated verifier accepts, and the transcript continues equally
+    from oracle import serialize as S
+    import importlib
+
+    blob = pcs.open_bytes(pts_dev, ch_abi)
+    assert blob == S.encode_opening(opened, proof), "ts_pcs_open bytes differ from the oracle's encoding"
+    opened_abi, proof_abi = importlib.import_module("tapstark_b200.proofio").decode_opening(blob)
+    assert [int(x) for x in ch_abi.sample()] == [int(x) for x in ch.clone().sample()]
     # (1)+(2): oracle's open
     alpha = [int(x) for x in och.sample_ef()]
     o_opened, o_reduced = V.pcs_open_reduced(pts_ora, log_blowup, alpha)
@@ -242,6 +252,10 @@ def check_pcs_open_verify(ts, ctx, orc, round_shapes, log_blowup, num_queries=6,
     for commit, (data, per_mat), (_, shapes), o_r in zip(commits, pts_dev, rounds_dev, opened):
         v_rounds.append((commit, [(ln, list(zip(pts, ys))) for (ln, _, _), pts, ys in zip(shapes, per_mat, o_r)]))
     assert V.pcs_verify(log_blowup, num_queries, pow_bits, v_rounds, proof, och_v.clone())
+    v_rounds_abi = []
+    for commit, (data, per_mat), (_, shapes), o_r in zip(commits, pts_dev, rounds_dev, opened_abi):
+        v_rounds_abi.append((commit, [(ln, list(zip(pts, [y.tolist() for y in ys]))) for (ln, _, _), pts, ys in zip(shapes, per_mat, o_r)]))
+    assert V.pcs_verify(log_blowup, num_queries, pow_bits, v_rounds_abi, proof_abi, och_v.clone())
     bad = proof.query_proofs[0].commit_phase_openings[0][0][0]
     bad[0] = (int(bad[0]) + 1) % P
     try:

@@ -147,6 +147,16 @@ def test_commit_phase(ts, ctx, orc):
     pc.check_commit_phase_rejects_high_degree(ts, ctx)
 
 
+@pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {}])
+def test_commit_phase_round_forms(ts, ctx, orc, monkeypatch, env):
+    """The three forms of a commit-phase round produce one transcript: chained on the device (sponge_step_kernel, beta read
+    by the fold kernel from device memory), the single-CTA tail, and the round-1 form with a host sponge per round."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pc.check_commit_phase(ts, ctx, orc, [12], 2, seed=31)
+    pc.check_commit_phase(ts, ctx, orc, [8, 6, 3], 1, seed=32)
+
+
 def test_commit_phase_golden(ts, ctx, orc, golden):
     import numpy as np
 
