@@ -311,6 +311,23 @@ def run_b200(a):
         e2e = {"value": elems / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes * world,
                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e}
         runner.release_host()
+        if world == 1 and hasattr(runner, "prepare_host"):
+            # the same call on a PAGEABLE host trace (a Rust Vec that was not registered with ts_host_register): the driver
+            # stages the copy through its own pinned buffers
+            try:
+                runner.prepare_host(pinned=False)
+                runner.step_e2e()
+                barrier()
+                ev0.record(stream)
+                for _ in range(2):
+                    runner.step_e2e()
+                ev1.record(stream)
+                barrier()
+                ms_p = ev0.elapsed_time(ev1) / 2
+                e2e["pageable_source"] = {"value": elems / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p, "steps": 2}
+            except TypeError:
+                pass
+            runner.release_host()
 
     if rank == 0:
         peaks = {}
@@ -432,8 +449,8 @@ class SingleGpuRunner:
         root, data = self.pcs.commit([(self.dom, self.trace)])
         return self._finish(root, data)
 
-    def prepare_host(self):
-        t = self.torch.empty((1 << self.log_rows, self.width), dtype=self.torch.int32, pin_memory=True)
+    def prepare_host(self, pinned=True):
+        t = self.torch.empty((1 << self.log_rows, self.width), dtype=self.torch.int32, pin_memory=pinned)
         t.copy_(self.trace_t)
         self.torch.cuda.synchronize()
         self.host_t = t

@@ -231,6 +231,26 @@ int ts_pcs_open(ts_ctx *ctx, const ts_tree *const *rounds, size_t n_rounds, cons
                 ts_challenger *chal, uint8_t **out_bytes, size_t *out_len);
 void ts_bytes_free(uint8_t *bytes);
 
+/* ---------------------------------------------------------------- TapTree commitment (f2, first slice)
+ * The commitment TapTreeMmcs really computes (basic/src/mmcs/taptree_mmcs.rs:101-114 -> basic/src/tcs/mod.rs:238-282): one
+ * Bitcoin script per leaf (tcs/mod.rs:197-225), BIP-341 TapLeaf hashes, a TapBranch tree of lexicographically sorted pairs
+ * and the leaf permutation that sorting causes (basic/src/tcs/builder.rs:38-93).
+ * Every leaf of a tree carries the same bit-commitment locking scripts around pushed integers, so the host passes the
+ * template once:  script(i) = seg[0] P(i) seg[1] P(x_1) ... P(x_{n_push-1}) seg[n_push],  P = minimal script-number push,
+ * x_k = canonical value of word push_word[k-1] of row i of `leaf_rows` (Montgomery on the device; for extension elements
+ * the host lists the limbs in the reversed order of tcs/mod.rs:214).  segs = the n_push + 1 segments concatenated,
+ * seg_offsets = n_push + 2 offsets.  The locking-script bytes themselves come from the external `bitcomm` crate (PARITY
+ * UNPINNED; oracle/taptree.py restates them from the in-tree twin scripts/src/bit_comm/*).  The reference repeats this
+ * commit num_queries times with fresh bit-commitments (tcs/mod.rs:284-292): call once per template.
+ * Outputs: root (32 bytes, as TapNodeHash serialises), the tree handle; leaf_indices[m] = position of Merkle leaf m among
+ * the TapTree's leaves (CompleteTaptree's reverse_idx_dict); ts_taptree_level downloads one level (0 = leaf hashes). */
+typedef struct ts_taptree ts_taptree;
+int ts_taptree_commit(ts_ctx *ctx, const ts_matrix *leaf_rows, const uint8_t *segs, const size_t *seg_offsets,
+                      const uint32_t *push_word, size_t n_push, uint8_t root[32], ts_taptree **out);
+int ts_taptree_leaf_indices(ts_ctx *ctx, const ts_taptree *t, uint32_t *out_host);
+int ts_taptree_level(ts_ctx *ctx, const ts_taptree *t, unsigned level, uint8_t *out_host);
+void ts_taptree_free(ts_taptree *t);
+
 /* ---------------------------------------------------------------- quotient values (f3)
  * quotient_values of uni_stark::prove (uni-stark/src/prover.rs:122-194) on the device-resident trace LDE:
  * for every point of the quotient domain g*H_m, m = 2^(log_n + log_quotient_degree) <= rows of the LDE, run the
@@ -291,6 +311,17 @@ int ts_device_free(ts_ctx *ctx, void *p);
 int ts_ipc_get_handle(ts_ctx *ctx, void *dev_ptr, uint8_t handle[64]);
 int ts_ipc_open(ts_ctx *ctx, const uint8_t handle[64], void **out);
 int ts_ipc_close(ts_ctx *ctx, void *p);
+/* Copy-engine transfers beside the kernels (no SM is taken from the LDE, unlike NCCL's copy kernels): dst/src may be this
+ * device's memory, a peer's IPC-mapped buffer (NVLink) or PINNED host memory (e.g. a column window of the host's
+ * row-major trace: ts_copy2d_async with src_pitch = full row bytes).  The copy runs on transfer stream `lane` (0..7:
+ * independent queues, e.g. lane 0 host staging, lanes 1..7 peer copies spread over the copy engines); after_main != 0 orders it after everything queued on the
+ * context stream so far.  ts_copy_join makes the context stream wait for all transfers issued on that lane so far.
+ * Across ranks the caller still needs one collective before reading what PEERS wrote (e.g. a 4-byte all-reduce after
+ * ts_copy_join). */
+int ts_copy_async(ts_ctx *ctx, int lane, void *dst, const void *src, size_t bytes, int after_main);
+int ts_copy2d_async(ts_ctx *ctx, int lane, void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                    size_t width_bytes, size_t rows, int after_main);
+int ts_copy_join(ts_ctx *ctx, int lane);
 /* alpha^0 .. alpha^(count-1) (+16 zero entries) as a device matrix, computed once per opening */
 int ts_alpha_powers(ts_ctx *ctx, const uint32_t alpha_monty[4], size_t count, ts_matrix **out);
 /* acc (+)= sum_c alpha^(first_power + c) * m[:, c]; a row shard whose columns arrive as several blocks calls it
@@ -301,6 +332,20 @@ int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const ts_matrix *alph
  * when they have equal power-of-two widths (the column blocks of the all-to-all), else one pass per block. */
 int ts_dot_ext_powers_blocks(ts_ctx *ctx, ts_matrix *const *blocks, size_t n_blocks, const ts_matrix *alpha_powers,
                              ts_matrix *acc);
+/* Chained commit-phase rounds of a ROW-SHARDED layer (fri/src/prover.rs:112-126 per round): nothing returns to the host
+ * between rounds.  After whole digests have been observed the BfChallenger state is (root, previous squeeze), so one small
+ * kernel per round combines the ranks' sub-roots into the layer root (top log2(n_sub) levels), advances the sponge
+ * (h = Blake3(root || h_prev)) and leaves beta/2 in device memory, where the fold of that round reads it.
+ *   begin : device state initialised from the host challenger (TS_ERR_ARG if it holds partially observed input)
+ *   step  : sub_roots_dev = n_sub x 32 bytes in rank order (the caller's all-gather), round = 0, 1, ...
+ *   fold  : ts_fri_fold_ext_shard with this round's beta taken from the chain
+ *   end   : ONE read-back of all layer roots; the host challenger replays observe/sample per round; commits_out
+ *           (n_rounds x 32 bytes) may be NULL; frees the chain. */
+int ts_fri_chain_begin(ts_ctx *ctx, const ts_challenger *chal, size_t max_rounds, uint32_t **chain_dev);
+int ts_fri_chain_step(ts_ctx *ctx, uint32_t *chain_dev, const uint8_t *sub_roots_dev, size_t n_sub, size_t round);
+int ts_fri_fold_ext_shard_chain(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                                const uint32_t *chain_dev, const uint32_t *addend_dev, uint32_t *out_dev);
+int ts_fri_chain_end(ts_ctx *ctx, uint32_t *chain_dev, ts_challenger *chal, size_t n_rounds, uint8_t *commits_out);
 /* fold rows [first, first + h_local) of a layer of h_global rows (fold_matrix on a contiguous row range);
  * addend_dev (may be NULL) is the matching slice of the next FRI input. */
 int ts_fri_fold_ext_shard(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,

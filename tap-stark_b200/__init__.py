@@ -127,6 +127,17 @@ _SIGNATURES = {
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
     "ts_pcs_open": (C.c_int, [_vp, _vpp, C.c_size_t, _szp, _vp, C.c_uint, C.c_uint, C.c_uint, _vp, _vpp, _szp]),
     "ts_bytes_free": (None, [_vp]),
+    "ts_taptree_commit": (C.c_int, [_vp, _vp, _vp, _szp, _vp, C.c_size_t, _u8p, _vpp]),
+    "ts_taptree_leaf_indices": (C.c_int, [_vp, _vp, _vp]),
+    "ts_taptree_level": (C.c_int, [_vp, _vp, C.c_uint, _vp]),
+    "ts_taptree_free": (None, [_vp]),
+    "ts_copy_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_size_t, C.c_int]),
+    "ts_copy2d_async": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
+    "ts_copy_join": (C.c_int, [_vp, C.c_int]),
+    "ts_fri_chain_begin": (C.c_int, [_vp, _vp, C.c_size_t, _vpp]),
+    "ts_fri_chain_step": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t]),
+    "ts_fri_fold_ext_shard_chain": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
+    "ts_fri_chain_end": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ts_dft_batch_host": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.c_size_t, C.c_uint32, _vp]),
     "ts_host_register": (C.c_int, [_vp, _vp, C.c_size_t]),
     "ts_host_unregister": (C.c_int, [_vp, _vp]),
@@ -192,6 +203,7 @@ class Context:
         if rc != 0:
             raise TapStarkError(f"ts_ctx_create failed (rc={rc}): no usable CUDA device; there is no CPU fallback")
         self._h = h
+        self.stream = stream  # the caller's cudaStream_t handle, or None for the context's private stream
 
     def check(self, rc: int, what: str = ""):
         if rc != 0:
@@ -509,6 +521,49 @@ class BfChallenger:
     def __del__(self):
         try:
             self._L.ts_challenger_free(self._h)
+        except Exception:
+            pass
+
+
+class TapTreeCommit:
+    """basic::tcs::TCS::commit_polys on the device (first slice of SURVEY f2): TapLeaf hashes of the templated leaf scripts,
+    the sorted-pair TapBranch tree and CompleteTaptree's leaf index table.  `segments` / `push_word` describe the leaf script
+    template (include/tapstark.h: ts_taptree_commit); `rows` is a DeviceMatrix with one row of field words per leaf."""
+
+    def __init__(self, ctx: Context, rows: DeviceMatrix, segments: Sequence[bytes], push_word: Sequence[int]):
+        self.ctx = ctx
+        n_push = len(push_word) + 1
+        if len(segments) != n_push + 1:
+            raise TapStarkError("taptree: need one segment more than pushes")
+        blob = b"".join(segments)
+        offs = [0]
+        for s_ in segments:
+            offs.append(offs[-1] + len(s_))
+        seg_off = (C.c_size_t * len(offs))(*offs)
+        pw = np.asarray(list(push_word) or [0], dtype=np.uint32)
+        root = (C.c_uint8 * 32)()
+        h = C.c_void_p()
+        ctx.check(ctx._L.ts_taptree_commit(ctx._h, rows._h, C.c_char_p(blob), seg_off, _ptr(pw), n_push, root, C.byref(h)), "taptree_commit")
+        self._h, self.root, self.n_leaves = h, bytes(root), rows.rows
+
+    def leaf_indices(self) -> np.ndarray:
+        out = np.empty(self.n_leaves, dtype=np.uint32)
+        self.ctx.check(self.ctx._L.ts_taptree_leaf_indices(self.ctx._h, self._h, _ptr(out)), "taptree_leaf_indices")
+        return out
+
+    def level(self, level: int) -> np.ndarray:
+        out = np.empty((self.n_leaves >> level, 32), dtype=np.uint8)
+        self.ctx.check(self.ctx._L.ts_taptree_level(self.ctx._h, self._h, level, _ptr(out)), "taptree_level")
+        return out
+
+    def free(self):
+        if self._h:
+            self.ctx._L.ts_taptree_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
         except Exception:
             pass
 

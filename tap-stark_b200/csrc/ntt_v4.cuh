@@ -238,3 +238,257 @@ __global__ void fill_pre_table_kernel(uint2 *dst, const uint2 *pre, int D, int b
 }
 
 }  // namespace ntt4
+
+// =====================================================================================================================
+// TMA variant of the contiguous-source passes (P2, P4): the 64 KiB tile is staged by `cp.async.bulk.tensor` (one elected
+// thread, one bulk tensor copy per 4-column plane, completion on an mbarrier) instead of 16 LDG.128 per thread.  The
+// source is a blocked matrix [col / 8][row][8 columns]; as a tensor it is {8 columns, 256 rows, rows / 256, column groups}
+// and the box {4, 256, 2^D / 256, 1} is exactly one plane of the position-major tile: row p of the plane lands at 16-byte
+// unit p (profiles/tools/tma_probe.cu checks this on the GPU).  The hardware swizzle modes cannot produce the tile's
+// sigma(p): with a 16- or 32-byte inner box CU_TENSOR_MAP_SWIZZLE_128B faults (the box row is narrower than the swizzle
+// span; same probe), so the plane is staged UNSWIZZLED and the first round, which reads 32 consecutive units per warp
+// instruction (conflict free as they are), writes its results into the swizzled layout the other rounds use.
+// Opt-in (TS_TMA=1): measured against the LDG form in profiles/r02/README.md.  Device builds only.
+#ifndef TS_EMULATE
+#include <cuda.h>
+
+namespace ntt4 {
+
+TS_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TS_D void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+TS_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+TS_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+TS_D void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// first round out of the TMA-staged tile: plane h holds row p at unit (h << D) + p.  Lanes walk 32 consecutive groups of one
+// plane and the results go to the swizzled layout of the other rounds, unit hx(h) ^ sigma(g) + 256 c: that is the staged
+// unit of group g' = sigma(g) ^ s3(h), which differs from g in its low three bits only -- an item of the SAME warp reads it
+// in this iteration, hence the __syncwarp between the loads and the stores.
+template <int D, bool INV, int NT, int NQv = dnq(D)>
+TS_D void r1_sm(uint4 *tile, const FastTables &t, int tid) {
+    using G = Geo<D, NQv>;
+    constexpr int LOGR = G::LOGR1, R = 1 << LOGR;
+    constexpr int ITEMS = 256 * G::NQ;
+    static_assert(ITEMS % NT == 0 && NT % 32 == 0 && 256 % NT == 0 || NT % 256 == 0, "r1_sm: thread count");
+    TS_NOUNROLL
+    for (int k = 0; k < ITEMS / NT; k++) {
+        const uint32_t item = (uint32_t)(tid + k * NT), g = item & 255, h = item >> 8;
+        const uint32_t src0 = (h << D) + g;
+        V4 x[R];
+        TS_UNROLL
+        for (int c = 0; c < R; c++) x[c] = ld4(tile + src0 + 256 * c);
+        __syncwarp();
+        dft_v4<LOGR, INV, true>(x);
+        TS_UNROLL
+        for (int i = 1; i < R; i++) x[i] = vmul(x[i], rtw<INV, false, D, 8>(t, nullptr, g, (uint32_t)brev_c(i, LOGR), i));
+        const uint32_t b0 = hx<D>(h) ^ sigma(g);
+        TS_UNROLL
+        for (int c = 0; c < R; c++) st4(tile + b0 + 256 * c, x[c]);
+    }
+}
+
+// ---- warp-shuffle exchange between the last two rounds (TS_SHFL=1) ---------------------------------------------------------
+// R3 (radix 8, stride 4) leaves a thread with the 8 positions 32 blk + g + 4 c of one quad; R4 (radix 4, stride 1) wants the
+// 4 positions 4 blk4 + c' with blk4 = 8 blk + c and c' = g.  The four lanes g = 0..3 of a group (lane bits 1..2; bit 0 is the
+// quad) therefore hold an 8 x 4 block that has to be transposed: two butterfly exchanges (__shfl_xor by 4, then by 2), after
+// which lane t owns the R4 items c = 2t and 2t + 1.  No shared-memory round trip and no barrier between R3 and R4 --
+// at the price of 32 SHFL + 64 SEL per 32 elements where the shared-memory form issues 16 LDS/STS.128
+// (profiles/r02/README.md has the measured comparison).
+TS_D V4 shfl4(const V4 &a, int mask) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = __shfl_xor_sync(0xffffffffu, a.v[k], mask);
+    return r;
+}
+TS_D V4 sel4(bool p, const V4 &a, const V4 &b) {
+    V4 r;
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) r.v[k] = p ? a.v[k] : b.v[k];
+    return r;
+}
+template <int D, bool INV, bool POST, int NT, int NQv = dnq(D)>
+TS_D void r34_shfl_st(uint4 *tile, char *dst_h, bool valid, size_t row_base, int log_stride, size_t pitch_b, const FastTables &t,
+                      const uint2 *post, int tid) {
+    using G = Geo<D, NQv>;
+    static_assert(G::NQ == 2, "r34_shfl_st: lane bit 0 = quad, bits 1..2 = g (D = 11 tiles)");
+    constexpr int ITEMS = (G::L / 8) * G::NQ;
+    static_assert(ITEMS % NT == 0, "r34_shfl_st: thread count");
+    const size_t step = ((size_t)1 << log_stride) * pitch_b;
+    TS_NOUNROLL
+    for (int k = 0; k < ITEMS / NT; k++) {
+        const uint32_t item = (uint32_t)(tid + k * NT);
+        const uint32_t h = item & 1u, g = (item >> 1) & 3u, blk = item >> 3;  // lanes: quad, then g, then block
+        const uint32_t base = hx<D>(h) ^ ((blk << 5) | g) ^ ((blk & 1u) << 2);
+        V4 x[8];
+        TS_UNROLL
+        for (int c = 0; c < 8; c++) x[c] = ld4(tile + (base ^ (uint32_t)((4 * c) ^ ((c >> 1) & 3))));
+        dft_v4<3, INV, true>(x);
+        TS_UNROLL
+        for (int i = 1; i < 8; i++) x[i] = vmul(x[i], rtw<INV, false, 5, 2>(t, nullptr, g, (uint32_t)brev_c(i, 3), i));
+        // the shared-memory form stores register c to position 32 blk + g + 4 c: "digit c" below is register c
+        // exchange A (g bit 1): keep digits [0,4) or [4,8), receive the partner's same digits
+        const bool hiA = (g & 2u) != 0;
+        V4 own[4], oth[4];
+        TS_UNROLL
+        for (int i = 0; i < 4; i++) {
+            const V4 send = sel4(hiA, x[i], x[i + 4]);
+            own[i] = sel4(hiA, x[i + 4], x[i]);
+            oth[i] = shfl4(send, 4);
+        }
+        // now own[i] / oth[i]: digit c = 4 hiA + i from lane g and from lane g ^ 2
+        const bool hiB = (g & 1u) != 0;
+        V4 y[2][4];  // y[kk][g'] : R4 item digit c = 2 t + kk, position c' = g'
+        TS_UNROLL
+        for (int kk = 0; kk < 2; kk++) {
+            // keep digits {2 hiB, 2 hiB + 1} of my half, send the other two
+            const V4 keep_own = sel4(hiB, own[2 + kk], own[kk]), keep_oth = sel4(hiB, oth[2 + kk], oth[kk]);
+            const V4 send_own = sel4(hiB, own[kk], own[2 + kk]), send_oth = sel4(hiB, oth[kk], oth[2 + kk]);
+            const V4 recv_own = shfl4(send_own, 2), recv_oth = shfl4(send_oth, 2);
+            // sources: keep_own from lane g, keep_oth from g ^ 2, recv_own from g ^ 1, recv_oth from g ^ 3.  Position g' wants the
+            // value of lane g' = g ^ m: low bit of m picks kept / received, high bit picks own / other (two select levels)
+            const V4 a_same = keep_own, a_flip = recv_own, b_same = keep_oth, b_flip = recv_oth;
+            TS_UNROLL
+            for (int gp = 0; gp < 4; gp++) {
+                const bool m0 = ((gp & 1) != 0) != hiB, m1 = ((gp & 2) != 0) != hiA;
+                y[kk][gp] = sel4(m1, sel4(m0, b_flip, b_same), sel4(m0, a_flip, a_same));
+            }
+        }
+        const uint32_t t4 = (g & 1u) * 1u + (g & 2u);  // lane's item pair index t = 2 hiA + hiB  (digits 4 hiA + 2 hiB + kk)
+        TS_UNROLL
+        for (int kk = 0; kk < 2; kk++) {
+            const uint32_t blk4 = 8 * blk + 2 * t4 + kk;
+            V4 z[4];
+            TS_UNROLL
+            for (int cp = 0; cp < 4; cp++) z[cp] = y[kk][cp];
+            dft_v4<2, INV, POST, 0>(z);
+            if (POST) {
+                const uint4 *pp = reinterpret_cast<const uint4 *>(post + 4 * blk4);
+                const uint4 pa = __ldg(pp), pb = __ldg(pp + 1);
+                z[0] = vmul(z[0], make_uint2(pa.x, pa.y));
+                z[1] = vmul(z[1], make_uint2(pa.z, pa.w));
+                z[2] = vmul(z[2], make_uint2(pb.x, pb.y));
+                z[3] = vmul(z[3], make_uint2(pb.z, pb.w));
+            }
+            if (valid) {
+                char *ptr = dst_h + (row_base + ((size_t)(4 * blk4) << log_stride)) * pitch_b;
+                TS_UNROLL
+                for (int cp = 0; cp < 4; cp++) st4(reinterpret_cast<uint4 *>(ptr + (size_t)cp * step), z[cp]);
+            }
+        }
+    }
+}
+
+template <int D, bool INV, bool MID, bool CSRC>
+__global__ void __launch_bounds__(V4_NT, 2) pass_shfl_kernel(PassParams p) {
+    TS_DYN_SMEM(uint4, tile);
+    using G = Geo<D>;
+    const int tid = threadIdx.x;
+    uint32_t cs, tile_id;
+    if (p.cs_shift >= 0) {
+        cs = blockIdx.x & ((1u << p.cs_shift) - 1);
+        tile_id = blockIdx.x >> p.cs_shift;
+    } else {
+        cs = blockIdx.x % p.n_col_slices;
+        tile_id = blockIdx.x / p.n_col_slices;
+    }
+    const uint32_t col = (cs << (14 - D)) + 4 * (tid & (G::NQ - 1));
+    const bool valid = col < p.ncols;
+    const uint32_t colc = valid ? col : 0;
+    const char *src_h = reinterpret_cast<const char *>(p.src) + col_off_bytes(colc, p.src_slice);
+    char *dst_h = reinterpret_cast<char *>(p.dst) + col_off_bytes(colc, p.dst_slice);
+    const size_t sp = row_pitch_bytes(p.src_pitch, p.src_slice), dp = row_pitch_bytes(p.dst_pitch, p.dst_slice);
+    size_t dst_base;
+    int dst_log_stride;
+    const uint2 *post = p.post;
+    if (MID) {
+        const uint32_t j = tile_id & ((1u << p.b) - 1), Kc = tile_id >> p.b;
+        dst_base = ((size_t)brev_bits(j, p.b) << p.m) + Kc;
+        dst_log_stride = p.klo_bits;
+        if (post) post += (((size_t)j << p.klo_bits) + Kc) << D;
+        r1_ld<D, INV, true, true, true, V4_NT>(tile, src_h, valid, (size_t)brev_bits(Kc, p.klo_bits) << D, 0, sp, p.t,
+                                               p.pre + ((size_t)j << D), tid);
+    } else {
+        const uint32_t lo = tile_id & ((1u << p.lo_bits) - 1), hi = tile_id >> p.lo_bits;
+        dst_base = ((size_t)hi << (p.lo_bits + D)) + lo;
+        dst_log_stride = p.lo_bits;
+        if (post) post += (size_t)lo << D;
+        r1_ld<D, INV, false, false, CSRC, V4_NT>(tile, src_h, valid, dst_base, p.lo_bits, sp, p.t, nullptr, tid);
+    }
+    __syncthreads();
+    nttp::dif_r2<D, INV, false, V4_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    // the quad a lane works on in the fused last rounds is lane bit 0 = tid & 1 = the quad of its column pointers
+    if (post) r34_shfl_st<D, INV, true, V4_NT>(tile, dst_h, valid, dst_base, dst_log_stride, dp, p.t, post, tid);
+    else r34_shfl_st<D, INV, false, V4_NT>(tile, dst_h, valid, dst_base, dst_log_stride, dp, p.t, nullptr, tid);
+}
+
+template <int D, bool INV>
+__global__ void __launch_bounds__(V4_NT, TS_V4_MINBLOCKS) pass_tma_kernel(PassParams p, const __grid_constant__ CUtensorMap src_map) {
+    extern __shared__ unsigned char tma_raw_[];
+    using G = Geo<D>;
+    // bulk tensor copies want a 128-byte aligned destination; 1024 keeps the planes on bank-row boundaries
+    // (offset added to the __shared__ base, so the compiler keeps LDS/STS instead of generic loads)
+    uint4 *tile = reinterpret_cast<uint4 *>(tma_raw_ + ((1024u - (smem_u32(tma_raw_) & 1023u)) & 1023u));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + G::UNITS);
+    const int tid = threadIdx.x;
+    uint32_t cs, tile_id;
+    if (p.cs_shift >= 0) {
+        cs = blockIdx.x & ((1u << p.cs_shift) - 1);
+        tile_id = blockIdx.x >> p.cs_shift;
+    } else {
+        cs = blockIdx.x % p.n_col_slices;
+        tile_id = blockIdx.x / p.n_col_slices;
+    }
+    const uint32_t col0 = cs << (14 - D);
+    const uint32_t col = col0 + 4 * (tid & (G::NQ - 1));
+    const bool valid = col < p.ncols;
+    char *dst_h = reinterpret_cast<char *>(p.dst) + col_off_bytes(valid ? col : 0, p.dst_slice);
+    const size_t dp = row_pitch_bytes(p.dst_pitch, p.dst_slice);
+    const uint32_t lo = tile_id & ((1u << p.lo_bits) - 1), hi = tile_id >> p.lo_bits;  // contiguous source: lo_bits == 0
+    const size_t row_base = ((size_t)hi << (p.lo_bits + D)) + lo;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        uint32_t planes = 0;
+        for (int h = 0; h < G::NQ; h++) planes += (col0 + 4 * h < p.ncols) ? 1u : 0u;
+        mbar_expect_tx(bar, planes * (uint32_t)(G::L * 16));
+        for (int h = 0; h < G::NQ; h++) {
+            const uint32_t ch = col0 + 4 * h;
+            if (ch < p.ncols) tma_load_4d(tile + ((size_t)h << D), &src_map, bar, (int)(ch & 7u), 0, (int)(row_base >> 8), (int)(ch >> 3));
+        }
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    mbar_wait(bar, 0);
+    r1_sm<D, INV, V4_NT>(tile, p.t, tid);
+    __syncthreads();
+    nttp::dif_r2<D, INV, false, V4_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    nttp::dif_r3<D, INV, false, V4_NT>(tile, p.t, nullptr, tid);
+    __syncthreads();
+    r4_st<D, INV, false, V4_NT>(tile, dst_h, valid, row_base, p.lo_bits, dp, nullptr, tid);
+}
+
+}  // namespace ntt4
+#endif  // !TS_EMULATE

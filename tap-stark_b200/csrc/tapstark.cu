@@ -26,6 +26,7 @@
 #include "ntt_v4.cuh"
 #include "open.cuh"
 #include "quotient.cuh"
+#include "sha256.cuh"
 
 // ------------------------------------------------------------------------------------------------ structs
 struct ts_matrix {
@@ -61,6 +62,11 @@ struct ts_ctx {
     // H2D pipeline of the host-buffer entry points: column chunks are copied on copy_stream while the previous
     // chunk's LDE runs on `stream`
     cudaStream_t copy_stream = nullptr;
+    // ts_copy_async / ts_copy2d_async: copy-engine transfers (peer buffers over NVLink, strided host windows) on their own
+    // stream, ordered after the work queued on `stream` at the call; ts_copy_join makes `stream` wait for them
+    static constexpr int XFER_LANES = 8;  // independent queues (e.g. lane 0 host staging, lanes 1..7 one per peer)
+    cudaStream_t xfer_stream[XFER_LANES] = {};
+    cudaEvent_t ev_xfer_in[XFER_LANES] = {}, ev_xfer_out[XFER_LANES] = {};
     // second compute stream: the leaf hash of column chunk k runs here beside the LDE of chunk k+1 (lde_hash_overlapped)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side = nullptr;
@@ -668,12 +674,82 @@ int launch_v4(ts_ctx *c, int kind, const ntt4::PassParams &p, size_t blocks) {  
     }
     return check_launch(c, "ntt4::pass_kernel");
 }
+#ifndef TS_EMULATE
+// TMA form of the contiguous-source passes (ntt_v4.cuh: pass_tma_kernel); TS_TMA=1
+bool use_tma() { return getenv("TS_TMA") != nullptr; }  // read per call: tests and A/B runs flip it inside one process
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+template <int D>
+int launch_v4_tma(ts_ctx *c, bool inverse, const ntt4::PassParams &p, size_t blocks, size_t rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) TS_FAIL(c, TS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    // blocked source [col / 8][row][8] as a 4-D tensor {8 columns, 256 rows, rows / 256, column groups}
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {8, 256, rows / 256, (p.ncols + 7) / 8};
+    const cuuint64_t strides[3] = {32, 32 * 256, (cuuint64_t)p.src_slice * 4};
+    const cuuint32_t box[4] = {4, 256, (cuuint32_t)((1u << D) / 256), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<uint32_t *>(p.src), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) TS_FAIL(c, TS_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    const size_t smem = (size_t)16384 * 4 + 1024 + 16;
+    KScope ks(c, TS_K_NTT_PASS);
+    if (inverse) {
+        auto kfn = ntt4::pass_tma_kernel<D, true>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p, map);
+    } else {
+        auto kfn = ntt4::pass_tma_kernel<D, false>;
+        TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p, map);
+    }
+    return check_launch(c, "ntt4::pass_tma_kernel");
+}
+#endif
 int launch_v4_d(ts_ctx *c, int d, int kind, ntt4::PassParams &p, size_t tiles) {
     const size_t K = (size_t)1 << (14 - d);
     p.n_col_slices = (uint32_t)((p.ncols + K - 1) / K);
     p.cs_shift = log2_strict(p.n_col_slices);
     p.t = fast_tables(c);
     const size_t blocks = tiles * p.n_col_slices;
+#ifndef TS_EMULATE
+    if (d == 11 && getenv("TS_SHFL") != nullptr) {  // last two rounds exchanged through warp shuffles (A/B form, D = 11 tiles)
+        const size_t smem = (size_t)16384 * 4;
+        KScope ks(c, kind == 3 ? TS_K_LDE_MID : TS_K_NTT_PASS);
+        if (kind == 1) {
+            auto kfn = ntt4::pass_shfl_kernel<11, true, false, false>;
+            TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+        } else if (kind == 2) {
+            auto kfn = ntt4::pass_shfl_kernel<11, true, false, true>;
+            TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+        } else if (kind == 3) {
+            auto kfn = ntt4::pass_shfl_kernel<11, false, true, true>;
+            TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+        } else {
+            auto kfn = ntt4::pass_shfl_kernel<11, false, false, true>;
+            TS_LAUNCH(kfn, (unsigned)blocks, ntt4::V4_NT, smem, c->stream, p);
+        }
+        return check_launch(c, "ntt4::pass_shfl_kernel");
+    }
+    if (use_tma() && (kind == 2 || kind == 4) && p.src_slice != 0 && p.lo_bits == 0) {
+        const size_t rows = tiles << d;  // contiguous source: tiles * 2^d rows
+        switch (d) {
+            case 9: return launch_v4_tma<9>(c, kind == 2, p, blocks, rows);
+            case 10: return launch_v4_tma<10>(c, kind == 2, p, blocks, rows);
+            default: return launch_v4_tma<11>(c, kind == 2, p, blocks, rows);
+        }
+    }
+#endif
     switch (d) {
         case 9: return launch_v4<9>(c, kind, p, blocks);
         case 10: return launch_v4<10>(c, kind, p, blocks);
@@ -1247,6 +1323,18 @@ int ts_ctx_create(int device, void *stream, ts_ctx **out) {
     cudaFuncSetAttribute(ntt4::pass_kernel<11, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(ntt4::pass_kernel<11, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(ntt4::pass_kernel<11, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+#ifndef TS_EMULATE
+    cudaFuncSetAttribute(ntt4::pass_shfl_kernel<11, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_shfl_kernel<11, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_shfl_kernel<11, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_shfl_kernel<11, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+    cudaFuncSetAttribute(ntt4::pass_tma_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+#endif
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(nttp::ntt_pass_pm2_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
@@ -1317,6 +1405,13 @@ void ts_ctx_destroy(ts_ctx *c) {
         cudaEventDestroy(c->ev_side);
         cudaStreamDestroy(c->side_stream);
     }
+    for (int lane = 0; lane < ts_ctx::XFER_LANES; lane++)
+        if (c->xfer_stream[lane]) {
+            cudaStreamSynchronize(c->xfer_stream[lane]);
+            cudaEventDestroy(c->ev_xfer_in[lane]);
+            cudaEventDestroy(c->ev_xfer_out[lane]);
+            cudaStreamDestroy(c->xfer_stream[lane]);
+        }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int s = 0; s < 2; s++) {
@@ -2437,6 +2532,102 @@ int ts_ipc_close(ts_ctx *c, void *p) {
     TS_FAIL(c, TS_ERR_ARG, "ipc: not available in the emulated build");
 #endif
 }
+// ---- chained commit-phase rounds for a row-sharded layer (one process per GPU; collectives stay with the caller) -------
+static int xfer_ready(ts_ctx *c, int lane, bool after_main) {
+    if (lane < 0 || lane >= ts_ctx::XFER_LANES) TS_FAIL(c, TS_ERR_ARG, "copy: lane must be 0..7");
+#ifndef TS_EMULATE
+    if (!c->xfer_stream[lane]) {
+        TS_CUDA(c, cudaStreamCreateWithFlags(&c->xfer_stream[lane], cudaStreamNonBlocking));
+        TS_CUDA(c, cudaEventCreateWithFlags(&c->ev_xfer_in[lane], cudaEventDisableTiming));
+        TS_CUDA(c, cudaEventCreateWithFlags(&c->ev_xfer_out[lane], cudaEventDisableTiming));
+    }
+    if (after_main) {
+        TS_CUDA(c, cudaEventRecord(c->ev_xfer_in[lane], c->stream));
+        TS_CUDA(c, cudaStreamWaitEvent(c->xfer_stream[lane], c->ev_xfer_in[lane], 0));
+    }
+#else
+    (void)after_main;
+#endif
+    return TS_OK;
+}
+int ts_copy_async(ts_ctx *c, int lane, void *dst, const void *src, size_t bytes, int after_main) {
+    if (!c || !dst || !src) TS_FAIL(c, TS_ERR_ARG, "copy_async: null pointer");
+    TS_TRY(xfer_ready(c, lane, after_main != 0));
+#ifndef TS_EMULATE
+    TS_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->xfer_stream[lane]));
+#else
+    memmove(dst, src, bytes);
+#endif
+    return TS_OK;
+}
+int ts_copy2d_async(ts_ctx *c, int lane, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                    size_t rows, int after_main) {
+    if (!c || !dst || !src || width_bytes > dst_pitch || width_bytes > src_pitch) TS_FAIL(c, TS_ERR_ARG, "copy2d_async: bad argument");
+    TS_TRY(xfer_ready(c, lane, after_main != 0));
+#ifndef TS_EMULATE
+    TS_CUDA(c, cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, c->xfer_stream[lane]));
+#else
+    for (size_t r = 0; r < rows; r++) memmove((char *)dst + r * dst_pitch, (const char *)src + r * src_pitch, width_bytes);
+#endif
+    return TS_OK;
+}
+int ts_copy_join(ts_ctx *c, int lane) {
+    if (lane < 0 || lane >= ts_ctx::XFER_LANES) TS_FAIL(c, TS_ERR_ARG, "copy: lane must be 0..7");
+#ifndef TS_EMULATE
+    if (!c->xfer_stream[lane]) return TS_OK;
+    TS_CUDA(c, cudaEventRecord(c->ev_xfer_out[lane], c->xfer_stream[lane]));
+    TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_xfer_out[lane], 0));
+#endif
+    return TS_OK;
+}
+int ts_fri_chain_begin(ts_ctx *c, const ts_challenger *chal, size_t max_rounds, uint32_t **chain_dev) {
+    if (!c || !chal || !chain_dev) TS_FAIL(c, TS_ERR_ARG, "fri_chain_begin: null argument");
+    if (!chal->in_buf.empty()) TS_FAIL(c, TS_ERR_ARG, "fri_chain_begin: the challenger has partially observed input");
+    uint32_t *d = nullptr;
+    TS_CUDA(c, pool_alloc(c, (void **)&d, (12 + 8 * std::max<size_t>(max_rounds, 1)) * 4));
+    uint32_t h0[8];
+    memcpy(h0, &chal->state[8][0], 32);
+    cudaError_t e = cudaMemcpyAsync(d, h0, 32, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+        pool_release(c, d);
+        TS_FAIL(c, TS_ERR_CUDA, std::string("fri_chain_begin: ") + cudaGetErrorString(e));
+    }
+    *chain_dev = d;
+    return TS_OK;
+}
+int ts_fri_chain_step(ts_ctx *c, uint32_t *chain_dev, const uint8_t *sub_roots_dev, size_t n_sub, size_t round) {
+    if (!chain_dev || !sub_roots_dev || n_sub == 0 || n_sub > 32 || (n_sub & (n_sub - 1))) TS_FAIL(c, TS_ERR_ARG, "fri_chain_step: 1..32 sub-roots, a power of two");
+    KScope ks(c, TS_K_TREE);
+    auto kfn = ftail::sponge_step_kernel;
+    TS_LAUNCH(kfn, 1, 32, 0, c->stream, reinterpret_cast<const uint32_t *>(sub_roots_dev), (int)n_sub, chain_dev, chain_dev + 12 + 8 * round,
+              chain_dev + 8);
+    return check_launch(c, "sponge_step_kernel");
+}
+int ts_fri_fold_ext_shard_chain(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                                const uint32_t *chain_dev, const uint32_t *addend_dev, uint32_t *out_dev) {
+    const int lh = log2_strict(h_global);
+    if (!chain_dev || lh < 0 || lh > 26 || first + h_local > h_global) TS_FAIL(c, TS_ERR_ARG, "fold shard: bad range");
+    if (lh >= 8 && ((first | h_local) & 255)) TS_FAIL(c, TS_ERR_ARG, "fold shard: range must be a multiple of 256 rows");
+    if (lh < 8 && (first != 0 || h_local != h_global)) TS_FAIL(c, TS_ERR_ARG, "fold shard: small layers are not sharded");
+    return fold_ext_launch(c, in_dev, out_dev, addend_dev, lh, nullptr, first, h_local, chain_dev + 8);
+}
+int ts_fri_chain_end(ts_ctx *c, uint32_t *chain_dev, ts_challenger *chal, size_t n_rounds, uint8_t *commits_out) {
+    if (!chain_dev) return TS_OK;
+    std::vector<uint32_t> roots(8 * std::max<size_t>(n_rounds, 1));
+    cudaError_t e = cudaSuccess;
+    if (n_rounds) e = cudaMemcpyAsync(roots.data(), chain_dev + 12, n_rounds * 32, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    pool_release(c, chain_dev);
+    if (e != cudaSuccess) TS_FAIL(c, TS_ERR_CUDA, std::string("fri_chain_end: ") + cudaGetErrorString(e));
+    for (size_t r = 0; r < n_rounds && chal; r++) {  // the host challenger replays the rounds (prover.rs:114-116)
+        const uint8_t *root = reinterpret_cast<const uint8_t *>(roots.data() + 8 * r);
+        if (commits_out) memcpy(commits_out + 32 * r, root, 32);
+        ts_challenger_observe_digest(chal, root);
+        uint32_t beta[4];
+        ts_challenger_sample_ext(chal, beta);
+    }
+    return TS_OK;
+}
 int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev) {
     const int lh = log2_strict(h_global);
@@ -2717,6 +2908,116 @@ int ts_pcs_open(ts_ctx *c, const ts_tree *const *rounds, size_t n_rounds, const 
     return TS_OK;
 }
 void ts_bytes_free(uint8_t *p) { free(p); }
+
+
+// ---------------------------------------------------------------- TapTree commitment (f2, first slice)
+struct ts_taptree {
+    ts_ctx *ctx;
+    size_t n_leaves;
+    unsigned log_n;
+    uint32_t *nodes;     // all levels, leaves first: (2 n - 1) x 8 state words
+    uint8_t *swapped;    // n - 1 flags, level 0 first
+    uint32_t *leaf_idx;  // n: reverse_idx_dict
+};
+void ts_taptree_free(ts_taptree *t) {
+    if (!t) return;
+    pool_release(t->ctx, t->nodes);
+    pool_release(t->ctx, t->swapped);
+    pool_release(t->ctx, t->leaf_idx);
+    delete t;
+}
+static void be_bytes(const uint32_t w[8], uint8_t out[32]) {
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(w[i] >> 24), out[4 * i + 1] = (uint8_t)(w[i] >> 16), out[4 * i + 2] = (uint8_t)(w[i] >> 8), out[4 * i + 3] = (uint8_t)w[i];
+    }
+}
+int ts_taptree_commit(ts_ctx *c, const ts_matrix *leaf_rows, const uint8_t *segs, const size_t *seg_offsets, const uint32_t *push_word,
+                      size_t n_push, uint8_t root[32], ts_taptree **out) {
+    if (!c || !leaf_rows || !segs || !seg_offsets || !out || n_push == 0 || n_push > sha::MAX_PUSH) TS_FAIL(c, TS_ERR_ARG, "taptree: bad argument");
+    if (n_push > 1 && !push_word) TS_FAIL(c, TS_ERR_ARG, "taptree: push_word missing");
+    const size_t n = leaf_rows->rows;
+    const int log_n = log2_strict(n);
+    if (log_n < 0 || n > ((size_t)1 << 31)) TS_FAIL(c, TS_ERR_ARG, "taptree: the leaf count must be a power of two");  // builder.rs:40
+    for (size_t k = 1; k < n_push; k++)
+        if (push_word[k - 1] >= leaf_rows->width) TS_FAIL(c, TS_ERR_ARG, "taptree: push_word out of range");
+    const size_t total = seg_offsets[n_push + 1];
+    if (total > 0xffffffffu) TS_FAIL(c, TS_ERR_ARG, "taptree: template too long");
+    ts_taptree *t = new ts_taptree{c, n, (unsigned)log_n, nullptr, nullptr, nullptr};
+    uint8_t *d_segs = nullptr;
+    uint32_t *d_off = nullptr, *d_pw = nullptr;
+    auto fail = [&](int rc, const char *msg) {
+        if (msg) c->err = msg;
+        pool_release(c, d_segs), pool_release(c, d_off), pool_release(c, d_pw);
+        ts_taptree_free(t);
+        return rc;
+    };
+    if (pool_alloc(c, (void **)&t->nodes, (2 * n - 1) * 32) != cudaSuccess || pool_alloc(c, (void **)&t->swapped, std::max<size_t>(n - 1, 1)) != cudaSuccess ||
+        pool_alloc(c, (void **)&t->leaf_idx, n * 4) != cudaSuccess || pool_alloc(c, (void **)&d_segs, std::max<size_t>(total, 1)) != cudaSuccess ||
+        pool_alloc(c, (void **)&d_off, (n_push + 2) * 4) != cudaSuccess || pool_alloc(c, (void **)&d_pw, std::max<size_t>(n_push - 1, 1) * 4) != cudaSuccess)
+        return fail(TS_ERR_CUDA, "taptree: device allocation failed");
+    std::vector<uint32_t> off32(n_push + 2);
+    for (size_t k = 0; k < n_push + 2; k++) off32[k] = (uint32_t)seg_offsets[k];
+    cudaError_t e = cudaMemcpyAsync(d_segs, segs, total, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_push > 1) e = cudaMemcpyAsync(d_pw, push_word, (n_push - 1) * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return fail(TS_ERR_CUDA, cudaGetErrorString(e));
+    int rc;
+    {
+        sha::LeafParams p;
+        p.rows = leaf_rows->d, p.width = (uint32_t)leaf_rows->width, p.n_leaves = n, p.segs = d_segs, p.seg_off = d_off, p.push_word = d_pw;
+        p.n_push = (uint32_t)n_push, p.const_len = (uint32_t)total, p.out = t->nodes;
+        for (int i = 0; i < 8; i++) p.midstate[i] = sha::TAPLEAF_MID[i];
+        KScope ks(c, TS_K_HASH_LEAVES);
+        auto kfn = sha::taptree_leaf_kernel;
+        TS_LAUNCH(kfn, (unsigned)((n + sha::LEAF_NT - 1) / sha::LEAF_NT), sha::LEAF_NT, (size_t)16 * sha::LEAF_NT * 4, c->stream, p);
+        rc = check_launch(c, "taptree_leaf_kernel");
+    }
+    size_t in_off = 0, flag_off = 0;
+    for (size_t w = n; w > 1 && rc == TS_OK; w >>= 1) {
+        KScope ks(c, TS_K_TREE);
+        auto kfn = sha::taptree_branch_kernel;
+        TS_LAUNCH(kfn, (unsigned)((w / 2 + 255) / 256), 256, 0, c->stream, (const uint32_t *)(t->nodes + in_off * 8), w / 2,
+                  t->nodes + (in_off + w) * 8, t->swapped + flag_off);
+        rc = check_launch(c, "taptree_branch_kernel");
+        in_off += w;
+        flag_off += w / 2;
+    }
+    if (rc == TS_OK) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = sha::taptree_perm_kernel;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->num_sms * 8), 256, 0, c->stream, (const uint8_t *)t->swapped,
+                  (uint32_t)log_n, t->leaf_idx);
+        rc = check_launch(c, "taptree_perm_kernel");
+    }
+    uint32_t rw[8];
+    if (rc == TS_OK) {
+        e = cudaMemcpyAsync(rw, t->nodes + (2 * n - 2) * 8, 32, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return fail(TS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    pool_release(c, d_segs), pool_release(c, d_off), pool_release(c, d_pw);
+    d_segs = nullptr, d_off = nullptr, d_pw = nullptr;
+    if (rc != TS_OK) return fail(rc, nullptr);
+    if (root) be_bytes(rw, root);
+    *out = t;
+    return TS_OK;
+}
+int ts_taptree_leaf_indices(ts_ctx *c, const ts_taptree *t, uint32_t *out_host) {
+    TS_CUDA(c, cudaMemcpyAsync(out_host, t->leaf_idx, t->n_leaves * 4, cudaMemcpyDeviceToHost, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TS_OK;
+}
+int ts_taptree_level(ts_ctx *c, const ts_taptree *t, unsigned level, uint8_t *out_host) {
+    if (level > t->log_n) TS_FAIL(c, TS_ERR_ARG, "taptree: level out of range");
+    size_t off = 0;
+    for (unsigned l = 0; l < level; l++) off += t->n_leaves >> l;
+    const size_t cnt = t->n_leaves >> level;
+    std::vector<uint32_t> w(cnt * 8);
+    TS_CUDA(c, cudaMemcpyAsync(w.data(), t->nodes + off * 8, cnt * 32, cudaMemcpyDeviceToHost, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < cnt; i++) be_bytes(&w[8 * i], out_host + 32 * i);
+    return TS_OK;
+}
 
 void ts_blake3_host(const uint8_t *in, size_t len, uint8_t out[32]) { hostb3::hash(in, len, out); }
 

@@ -14,6 +14,7 @@
 #define TS_UNROLL
 #define TS_UNROLL2
 #define TS_NOUNROLL
+#define TS_UNROLL16
 #else
 #include <cuda_runtime.h>
 #define TS_DYN_SMEM(type, name)                                   \
@@ -22,6 +23,7 @@
 #define TS_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TS_UNROLL _Pragma("unroll")
 #define TS_NOUNROLL _Pragma("unroll 1")
+#define TS_UNROLL16 _Pragma("unroll 16")
 #ifndef TS_NO_LANE_UNROLL2
 #define TS_UNROLL2 _Pragma("unroll 2")
 #else

@@ -34,6 +34,20 @@ class ShardedProver:
         self.mmcs = ts.Blake3MerkleMmcs(ctx)
         self.cfg = ts.FriConfig(log_blowup, 16, 8, self.mmcs)
         self.use_batched_p2p = dist.get_backend() != "nccl"
+        import os
+
+        self.peer_lanes = max(1, min(7, int(os.environ.get("TS_PEER_LANES", "3"))))  # copy queues of the copy-engine re-shard
+        if "TS_REPLICATE_BELOW" in os.environ:  # measurement hook: FRI layers of at most this many elements are gathered
+            self.REPLICATE_BELOW = int(os.environ["TS_REPLICATE_BELOW"])
+        if device.type == "cuda":
+            # torch tensors, the NCCL collectives and the caching allocator's frees are ordered on torch's current stream; the
+            # library's kernels run on the context's stream.  They must be ONE stream ("Multi-GPU"): a
+            # context with a private stream would let the all-to-all read an LDE that is still being written.
+            cur = torch.cuda.current_stream(device).cuda_stream
+            if ctx.stream is None or int(ctx.stream) != int(cur):
+                raise ts.TapStarkError(
+                    "ShardedProver: create the Context on torch's current stream (ts.Context(device, "
+                    "torch.cuda.current_stream().cuda_stream)) and keep that stream current while proving")
 
     # ---- plumbing -------------------------------------------------------------------------------------
     def _wrap(self, t, rows, width):
@@ -73,8 +87,10 @@ class ShardedProver:
         if key in cache:
             return cache[key]
         torch, dist, ctx, L, G, r = self.torch, self.dist, self.ctx, self.ctx._L, self.world, self.rank
-        # opt-in: measured SLOWER than the chunk-overlapped NCCL all-to-all on 2/4/8 B200s (profiles/r01/README.md)
-        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("TS_P2P", "0") == "1" and G <= 8
+        # peer-mapped receive buffers serve two forms of the re-shard (self.reshard_mode()): "ce" = copy-engine peer copies
+        # beside the next chunk's LDE (default), "fused" = the last butterfly pass stores straight into them (TS_P2P=1,
+        # measured slower in round 1); "nccl" needs none
+        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and self.reshard_mode() in ("ce", "fused") and G <= 8
         Nl = N // G
         bases, handles = [], []
         if ok:
@@ -103,6 +119,7 @@ class ShardedProver:
                             ok = False
                             break
                         base_d = q_.value
+                        self.__dict__.setdefault("_p2p_mapped", []).append(base_d)
                     owners[d] = base_d + r * Nl * wc * 4  # my block inside rank d's [G, Nl, wc] buffer
                 if not ok:
                     break
@@ -111,6 +128,26 @@ class ShardedProver:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # everyone or no one; also: all mappings exist before the first store
         cache[key] = plan if int(flag.item()) == 1 else None
         return cache[key]
+
+    def reshard_mode(self) -> str:
+        """How LDE rows travel to their owners.  TS_RESHARD = ce | nccl | fused (TS_P2P=1 is the round-1 spelling of fused)."""
+        import os
+
+        if os.environ.get("TS_P2P", "0") == "1":
+            return "fused"
+        return os.environ.get("TS_RESHARD", "ce")
+
+    def close(self):
+        """Releases the peer-mapped receive buffers of the fused re-shard (TS_P2P=1): closes the IPC mappings of the other
+        ranks' buffers and frees this rank's own.  Collective-free; call after the last step."""
+        L, ctx = self.ctx._L, self.ctx
+        for plan in self.__dict__.pop("_p2p_cache", {}).values():
+            if not plan:
+                continue
+            for own_base, _owners in plan:
+                L.ts_device_free(ctx._h, C.c_void_p(own_base))
+        for p_ in self.__dict__.pop("_p2p_mapped", []):
+            L.ts_ipc_close(ctx._h, C.c_void_p(p_))
 
     def combine_roots(self, data) -> bytes:
         """all-gather the G sub-roots (device to device: the sub-root never visits the host on its own) and hash the
@@ -144,7 +181,9 @@ class ShardedProver:
 
         cmax = int(os.environ.get("TS_SHARD_CHUNKS", "4"))  # measurement hook
         c = 1
-        while c < cmax and wl % (2 * c) == 0 and wl // (2 * c) >= 8 and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0:
+        # the row hash takes at most 32 equal-width column blocks (b3::MAX_SEG, fold::DOT_MAX_SEG): G * chunks <= 32
+        while (c < cmax and 2 * c * self.world <= 32 and wl % (2 * c) == 0 and wl // (2 * c) >= 8
+               and (wl // (2 * c)) & (wl // (2 * c) - 1) == 0):
             c *= 2
         return c if self.world > 1 else 1
 
@@ -162,13 +201,17 @@ class ShardedProver:
             panels.append(t)
         return panels
 
-    def commit_and_fri(self, trace_t, host_panels=None):
+    def commit_and_fri(self, trace_t, host_panels=None, host_full=None):
         """trace_t: torch int32 [n, w/G] -- this rank's columns of the trace (Montgomery-form bits), resident; or
-        host_panels (see host_panels()): the same data in pinned host memory, copied H2D inside the step.
+        host_panels (see host_panels()): the same data in pinned host memory as per-chunk panels; or host_full: the WHOLE
+        row-major n x w trace in pinned host memory (what a RowMajorMatrix is), of which this rank copies its column
+        windows with strided 2-D copies inside the step.
         Returns dict(root, commits, final_poly, rounds); identical on every rank."""
         ts, ctx, torch, dist, G, r, b = self.ts, self.ctx, self.torch, self.dist, self.world, self.rank, self.b
         L = ctx._L
-        if host_panels is not None:
+        if host_full is not None:
+            n, wl = host_full.shape[0], host_full.shape[1] // G
+        elif host_panels is not None:
             n, wl = host_panels[0].shape[0], sum(p_.shape[1] for p_ in host_panels)
         else:
             n, wl = trace_t.shape
@@ -178,9 +221,24 @@ class ShardedProver:
         wc = wl // C_
         gen = int(ts.to_monty(ts.GENERATOR))
         recv, works, keep = [], [], []
+        own_rows = []  # copy-engine re-shard: chunk c's LDE, whose rows [r*Nl, (r+1)*Nl) stay in place
         staged = []
         marks = [self._mark()]
-        if host_panels is not None:
+        if host_full is not None:
+            # strided column windows of the row-major pinned trace, transfer lane 0: window c+1 is copied while window c is
+            # transformed (ts_copy_join below makes the LDE of a window wait for exactly the copies issued before it)
+            W = host_full.shape[1]
+            for c in range(C_):
+                staged.append(torch.empty((n, wc), dtype=torch.int32, device=self.device))
+
+            def issue_h2d(c):
+                src = host_full.data_ptr() + (r * wl + c * wc) * 4
+                ctx.check(L.ts_copy2d_async(ctx._h, 0, C.c_void_p(staged[c].data_ptr()), wc * 4, C.c_void_p(src), W * 4, wc * 4, n,
+                                            1 if c == 0 else 0), "copy2d_async")
+
+            issue_h2d(0)
+            ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")
+        elif host_panels is not None:
             # all panels are queued on a side stream up front; the main stream waits panel by panel
             if not hasattr(self, "_copy_stream"):
                 self._copy_stream = torch.cuda.Stream()
@@ -194,22 +252,52 @@ class ShardedProver:
                     e_.record(self._copy_stream)
                     d_.record_stream(main)
                     staged.append((d_, e_))
+        mode = self.reshard_mode()
         plan = self._p2p_setup(N, wc, C_) if (G > 1 and n >= 1 << 18 and wc % 4 == 0) else None
         for c in range(C_):
-            if host_panels is not None:
+            if host_full is not None:
+                src_t = staged[c]
+                if c + 1 < C_:
+                    issue_h2d(c + 1)
+            elif host_panels is not None:
                 src_t, ev_ = staged[c]
                 torch.cuda.current_stream().wait_event(ev_)
             else:
                 src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
             ev = self._wrap(src_t, n, wc)
-            if plan is not None:
+            if plan is not None and mode == "fused":
                 # fused LDE + re-shard: the last butterfly pass writes each row range into its owner's buffer
                 ctx.check(L.ts_coset_lde_batch_scatter(ctx._h, ev._h, b, gen, plan[c][1], G, wc), "coset_lde_batch_scatter")
                 keep.append(src_t)
+                if host_full is not None and c + 1 < C_:
+                    ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")
                 continue
             lde_t = torch.empty((N, wc), dtype=torch.int32, device=self.device)
             lde = self._wrap(lde_t, N, wc)
             ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
+            if host_full is not None and c + 1 < C_:
+                ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")  # the next window must have landed before its LDE starts
+            if plan is not None:
+                # copy-engine re-shard (transfer lane 1): this rank's rows [d*Nl, (d+1)*Nl) of the chunk go to rank d's receive
+                # buffer over NVLink while the SMs run the next chunk's LDE; peers are visited starting after this rank so
+                # that no receiver is everybody's first target
+                blk = Nl * wc * 4
+                n_lanes = self.peer_lanes
+                pieces = max(1, -(-n_lanes // (G - 1)))  # keep n_lanes copy queues busy whatever the peer count
+                issued = set()
+                q = 0
+                for k in range(G - 1):  # this rank's own rows are hashed where they are: no self copy
+                    d = (r + 1 + k) % G
+                    for pc_ in range(pieces):
+                        lane = 1 + q % n_lanes
+                        q += 1
+                        lo, hi = blk * pc_ // pieces // 16 * 16, blk * (pc_ + 1) // pieces // 16 * 16 if pc_ + 1 < pieces else blk
+                        ctx.check(L.ts_copy_async(ctx._h, lane, C.c_void_p(plan[c][1][d] + lo), C.c_void_p(lde_t.data_ptr() + d * blk + lo),
+                                                  hi - lo, 0 if lane in issued else 1), "copy_async")
+                        issued.add(lane)
+                own_rows.append(lde_t)
+                keep.append((lde_t, src_t))
+                continue
             recv_t = torch.empty((G, Nl, wc), dtype=torch.int32, device=self.device)
             send_list, recv_list = list(lde_t.view(G, Nl, wc).unbind(0)), list(recv_t.unbind(0))
             if self.use_batched_p2p:
@@ -218,20 +306,27 @@ class ShardedProver:
                 works.append(dist.all_to_all(recv_list, send_list, async_op=True))  # overlaps the next chunk's LDE
             recv.append(recv_t)
             keep.append((lde_t, src_t))
+        marks_detail = [self._mark()]  # all LDE launches queued behind this point
         for w_ in works:
             w_.wait()
         if plan is not None:
+            if mode != "fused":
+                for lane in range(1, 1 + self.peer_lanes):
+                    ctx.check(L.ts_copy_join(ctx._h, lane), "copy_join")
             # every rank's stores into my buffers are complete once all ranks have passed this point in stream order
             if not hasattr(self, "_p2p_flag"):
                 self._p2p_flag = torch.zeros(1, device=self.device, dtype=torch.int32)
             dist.all_reduce(self._p2p_flag)
-        del keep
+        if not own_rows:
+            keep = None
         marks.append(self._mark())  # LDE + re-shard done
         # global column order: rank-major, then chunk
         blocks = []
         for s_ in range(G):
             for c in range(C_):
-                if plan is not None:
+                if plan is not None and own_rows and s_ == r:
+                    blocks.append(ts.DeviceMatrix.wrap_device(ctx, own_rows[c].data_ptr() + r * Nl * wc * 4, Nl, wc, keepalive=own_rows[c]))
+                elif plan is not None:
                     blocks.append(ts.DeviceMatrix.wrap_device(ctx, plan[c][0] + s_ * Nl * wc * 4, Nl, wc))
                 else:
                     blocks.append(self._wrap(recv[c][s_], Nl, wc))
@@ -251,10 +346,12 @@ class ShardedProver:
         ctx.check(L.ts_dot_ext_powers_blocks(ctx._h, arr, len(blocks), ap, fri._h), "dot_ext_powers_blocks")
         L.ts_matrix_free(ap)
         data.free()
+        blocks = own_rows = keep = None
         marks.append(self._mark())  # alpha reduction
         commits, final = self._fri_commit_phase(fri_t, N, ch)
         marks.append(self._mark())  # FRI commit phase
         self._marks = marks
+        self._marks_detail = marks_detail
         return {"root": root, "commits": commits, "final_poly": final, "rounds": len(commits)}
 
     PHASES = ("lde_and_reshard", "hash_tree_roots", "alpha_reduction", "fri_commit_phase")
@@ -272,7 +369,11 @@ class ShardedProver:
         if not m or m[0] is None:
             return None
         m[-1].synchronize()
-        return {k: m[i].elapsed_time(m[i + 1]) for i, k in enumerate(self.PHASES)}
+        out = {k: m[i].elapsed_time(m[i + 1]) for i, k in enumerate(self.PHASES)}
+        d = getattr(self, "_marks_detail", None)
+        if d and d[0] is not None:
+            out["lde_kernels_done_at"] = m[0].elapsed_time(d[0])  # the rest of lde_and_reshard is the exposed exchange + barrier
+        return out
 
     def _fri_commit_phase(self, cur_t, len_g: int, ch):
         """fri/src/prover.rs:93-141 on a row-sharded codeword (cur_t: this rank's [len_g/G, 4] slice)."""
@@ -281,28 +382,44 @@ class ShardedProver:
         commits: List[bytes] = []
         local = cur_t.shape[0]
         blowup = 1 << self.b
-        while len_g > blowup:
+        # sharded rounds are CHAINED on the device (ts_fri_chain_*): sub-root all-gather -> root + sponge + beta in one small
+        # kernel -> fold reading beta from device memory; the host sees the roots once, after the last sharded round
+        sharded = 0
+        lg, lc = len_g, local
+        while lg > blowup and lg > self.REPLICATE_BELOW and (lc // 2) >= 256 and (lc // 2) * G == lg // 2:
+            sharded, lg, lc = sharded + 1, lg // 2, lc // 2
+        chain = C.c_void_p()
+        if sharded:
+            ctx.check(L.ts_fri_chain_begin(ctx._h, ch._h, sharded, C.byref(chain)), "fri_chain_begin")
+            buf = torch.empty((G + 1) * 32, dtype=torch.uint8, device=self.device)
+            mine = buf[G * 32 :]
+        for rnd in range(sharded):
             h_g, h_l = len_g // 2, local // 2
-            if len_g > self.REPLICATE_BELOW and h_l >= 256 and h_l * G == h_g:
-                leaves = self._wrap(cur_t, h_l, 8)
-                _, data = self.mmcs.commit([leaves], host_root=False)
-                root = self.combine_roots(data)
-                data.free()
-                commits.append(root)
-                ch.observe(root)
-                beta = ts.to_monty(ch.sample())
-                out_t = torch.empty((h_l, 4), dtype=torch.int32, device=self.device)
-                ctx.check(L.ts_fri_fold_ext_shard(ctx._h, C.c_void_p(cur_t.data_ptr()), h_g, r * h_l, h_l,
-                                                  beta.ctypes.data_as(C.c_void_p), None, C.c_void_p(out_t.data_ptr())),
-                          "fri_fold_ext_shard")
-                cur_t, len_g, local = out_t, h_g, h_l
-                continue
+            leaves = self._wrap(cur_t, h_l, 8)
+            _, data = self.mmcs.commit([leaves], host_root=False)
+            data.root_to_device(mine.data_ptr())
+            data.free()
+            dist.all_gather_into_tensor(buf[: G * 32], mine)
+            ctx.check(L.ts_fri_chain_step(ctx._h, chain, C.c_void_p(buf.data_ptr()), G, rnd), "fri_chain_step")
+            out_t = torch.empty((h_l, 4), dtype=torch.int32, device=self.device)
+            ctx.check(L.ts_fri_fold_ext_shard_chain(ctx._h, C.c_void_p(cur_t.data_ptr()), h_g, r * h_l, h_l, chain, None,
+                                                    C.c_void_p(out_t.data_ptr())), "fri_fold_ext_shard_chain")
+            cur_t, len_g, local = out_t, h_g, h_l
+        if len_g > blowup:
             # small layer: gather it everywhere and finish replicated (no further communication)
             full_t = torch.empty((len_g, 4), dtype=torch.int32, device=self.device)
             dist.all_gather_into_tensor(full_t.view(-1), cur_t.contiguous().view(-1))
+            if sharded:
+                cbuf = np.zeros((sharded, 32), dtype=np.uint8)
+                ctx.check(L.ts_fri_chain_end(ctx._h, chain, ch._h, sharded, cbuf.ctypes.data_as(C.c_void_p)), "fri_chain_end")
+                commits += [cbuf[i].tobytes() for i in range(sharded)]
             res = ts.bf_commit_phase(self.cfg, [self._wrap(full_t, len_g, 4)], ch, keep_data=False)
             commits += res.commits
             return commits, res.final_poly.tolist()
+        if sharded:
+            cbuf = np.zeros((sharded, 32), dtype=np.uint8)
+            ctx.check(L.ts_fri_chain_end(ctx._h, chain, ch._h, sharded, cbuf.ctypes.data_as(C.c_void_p)), "fri_chain_end")
+            commits += [cbuf[i].tobytes() for i in range(sharded)]
         # len_g <= blowup without ever gathering (only when the input was already tiny)
         parts = [torch.empty_like(cur_t) for _ in range(G)]
         dist.all_gather(parts, cur_t)
@@ -323,7 +440,7 @@ class ShardedRunner:
         self.rank, self.world = rank, world
         if width % world:
             raise ts.TapStarkError("width must be divisible by the number of GPUs")
-        self.n, self.wl, self.b = 1 << log_rows, width // world, log_blowup
+        self.n, self.wl, self.b, self.seed = 1 << log_rows, width // world, log_blowup, seed
         dev = torch.device("cuda", torch.cuda.current_device())
         # this rank's columns [rank*wl, (rank+1)*wl) of the ONE synthetic trace every N works on (element
         # (r, c) = SplitMix64((seed << 40) + r*width + c) mod p), so root and final polynomial are the 1-GPU ones
@@ -341,16 +458,28 @@ class ShardedRunner:
         return self.prover.commit_and_fri(self.trace_t)
 
     def prepare_host(self):
-        self.host_t = self.prover.host_panels(self.trace_t)
-        self.torch.cuda.synchronize()
+        """The boundary hands over ONE row-major n x width matrix (a RowMajorMatrix): every rank keeps a pinned host copy of
+        the whole trace and copies only its own column windows (strided 2-D copies) inside the timed step."""
+        torch, ts = self.torch, self.ts
+        n, W = self.n, self.wl * self.world
+        full = torch.empty((n, W), dtype=torch.int32, pin_memory=True)
+        tmp = torch.empty((n, self.wl), dtype=torch.int32, device="cuda")
+        for s_ in range(self.world):  # the same generator every rank uses for its resident shard
+            self.ctx.check(self.ctx._L.ts_fill_splitmix(self.ctx._h, tmp.data_ptr(), n, self.wl, self.seed, s_ * self.wl, W, 1),
+                           "fill_splitmix")
+            torch.cuda.current_stream().synchronize()
+            full[:, s_ * self.wl : (s_ + 1) * self.wl].copy_(tmp)
+        self.host_t = full
+        torch.cuda.synchronize()
 
     def step_e2e(self):
-        # this rank's column shard: pinned host panels -> HBM inside the step, overlapped with the LDE
-        return self.prover.commit_and_fri(None, host_panels=self.host_t)
+        # pinned row-major host trace -> this rank's column windows -> HBM inside the step, overlapped with the LDE
+        return self.prover.commit_and_fri(None, host_full=self.host_t)
 
     def release_host(self):
         self.host_t = None
 
     def close(self):
         self.trace_t = None
+        self.prover.close()
         self.ctx.trim()

@@ -36,13 +36,18 @@ def main():
         prover = ShardedProver(ts, ctx, rank, world, b, torch.device("cuda", local))
         prover.REPLICATE_BELOW = int(os.environ.get("TS_REPLICATE_BELOW", str(1 << 12)))
         out = {}
-        for name in ("resident", "resident_again", "host_panels"):
+        full_host = torch.from_numpy(ts.to_monty(trace).view(np.int32).copy()).pin_memory()
+        for name in ("resident", "resident_again", "host_panels", "host_full"):
             if name == "host_panels":
                 res = prover.commit_and_fri(None, host_panels=prover.host_panels(shard_t))
+            elif name == "host_full":
+                res = prover.commit_and_fri(None, host_full=full_host)
             else:
                 res = prover.commit_and_fri(shard_t)
             out[name] = {"root": res["root"].hex(), "commits": [c.hex() for c in res["commits"]], "final_poly": res["final_poly"]}
-        out["fused_p2p"] = any(v is not None for v in getattr(prover, "_p2p_cache", {}).values())
+        out["reshard"] = prover.reshard_mode()
+        out["peer_buffers"] = any(v is not None for v in getattr(prover, "_p2p_cache", {}).values())
+        prover.close()
         torch.cuda.synchronize()
     Path(f"{out_path}.{rank}").write_text(json.dumps(out))
     dist.barrier()

@@ -71,6 +71,23 @@ def test_dft_family(ts, ctx, orc, log_n, width):
     pc.check_dft_family(ts, ctx, orc, log_n, width)
 
 
+@pytest.mark.parametrize("log_n,width,b", [(18, 8, 2), (19, 24, 1), (20, 16, 2), (21, 12, 1), (22, 8, 1)])
+def test_lde_tma_staging(ts, ctx, orc, monkeypatch, log_n, width, b):
+    """TS_TMA=1: the contiguous-source passes stage their tile with cp.async.bulk.tensor (ntt_v4.cuh pass_tma_kernel,
+    128-byte hardware swizzle = the tile's own sigma): every LDE word equals the oracle's, for digits 9, 10 and 11 and a
+    ragged last column slice."""
+    monkeypatch.setenv("TS_TMA", "1")
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
+@pytest.mark.parametrize("log_n,width,b", [(22, 8, 1), (21, 12, 2)])
+def test_lde_shuffle_exchange(ts, ctx, orc, monkeypatch, log_n, width, b):
+    """TS_SHFL=1: the exchange between the last two rounds of a D = 11 tile goes through __shfl_xor (ntt_v4.cuh
+    r34_shfl_st) instead of shared memory; same LDE words."""
+    monkeypatch.setenv("TS_SHFL", "1")
+    pc.check_lde(ts, ctx, orc, log_n, width, b)
+
+
 def test_lde_config2_shape_column_subset(ts, ctx, orc):
     """BASELINE config 2 (2^20 x 64, log_blowup 2): the LDE is column-independent, so the oracle LDE of a column
     subset must equal the same columns of the full device result; plus the low-coset property

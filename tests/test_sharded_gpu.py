@@ -1,6 +1,6 @@
 """The N>1 path on real GPUs (needs >= 2 devices; skipped otherwise): NCCL ranks of tap-stark_b200/parallel.py with the
-default NCCL all-to-all re-shard and, with TS_P2P=1, the fused LDE + re-shard (last butterfly pass storing into
-peer-mapped buffers); both must reproduce the single-process oracle transcript bit for bit."""
+three forms of the re-shard (copy-engine peer copies, NCCL all-to-all, fused LDE + peer stores); all must reproduce the
+single-process oracle transcript bit for bit."""
 import json
 import os
 import subprocess
@@ -31,17 +31,21 @@ def run_world(tmp_path, world, log_n, width, b, extra_env):
     return [json.loads(Path(f"{out}.{k}").read_text()) for k in range(world)]
 
 
-@pytest.mark.parametrize("p2p", ["1", "0"])
-def test_sharded_gpu_matches_oracle(tmp_path, orc, p2p):
+@pytest.mark.parametrize("mode", ["ce", "nccl", "fused"])
+def test_sharded_gpu_matches_oracle(tmp_path, orc, mode):
+    """ce: copy-engine peer copies into IPC-mapped receive buffers (default); nccl: all-to-all; fused: the last butterfly
+    pass stores into the peers' buffers.  Resident shard, per-chunk host panels and the row-major host trace (strided
+    windows) all give the single-process oracle transcript."""
     if n_gpus() < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 4 if n_gpus() >= 4 else 2
     log_n, width, b = 18, 64, 2  # 16 or 32 columns per rank -> 2 or 4 chunks of 8
-    results = run_world(tmp_path, world, log_n, width, b, {"TS_P2P": p2p})
+    results = run_world(tmp_path, world, log_n, width, b, {"TS_RESHARD": mode})
     root, commits, final = oracle_transcript(orc, log_n, width, b)
     for res in results:
-        assert res["fused_p2p"] == (p2p == "1")
-        for name in ("resident", "resident_again", "host_panels"):
+        assert res["reshard"] == mode
+        assert res["peer_buffers"] == (mode != "nccl")
+        for name in ("resident", "resident_again", "host_panels", "host_full"):
             assert res[name]["root"] == root, name
             assert res[name]["commits"] == commits, name
             assert res[name]["final_poly"] == final, name
