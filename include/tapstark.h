@@ -332,6 +332,26 @@ int ts_dot_ext_powers_acc(ts_ctx *ctx, const ts_matrix *m, const ts_matrix *alph
  * when they have equal power-of-two widths (the column blocks of the all-to-all), else one pass per block. */
 int ts_dot_ext_powers_blocks(ts_ctx *ctx, ts_matrix *const *blocks, size_t n_blocks, const ts_matrix *alpha_powers,
                              ts_matrix *acc);
+/* ALL row-sharded commit-phase rounds of a step in one call, the sub-root exchange inside the kernels: every rank owns a
+ * MAILBOX (ts_fri_mailbox_words() u32 of zero-filled device memory, e.g. from ts_device_malloc) that its peers map with
+ * ts_ipc_open; mailboxes[s] is rank s's mailbox as seen from this process (mailboxes[rank] = its own).  Per round: leaf
+ * hash + subtree, the sub-root is stored into every rank's mailbox (NVLink), the sponge step starts when all sub-roots of
+ * the round have arrived, the fold reads beta from device memory.  epoch: any value that differs from the previous call's
+ * (a step counter), the same on every rank.  cur_dev: this rank's rows of the layer (len_global / world extension
+ * elements); out_dev receives its rows after n_rounds folds.  The host challenger replays the rounds at the end, as in
+ * ts_fri_chain_end; commits_out = n_rounds x 32 bytes. */
+int ts_fri_mailbox_words(void);
+int ts_fri_commit_phase_sharded(ts_ctx *ctx, const uint32_t *cur_dev, size_t len_global, size_t rank, size_t world,
+                                size_t n_rounds, uint32_t *const *mailboxes, uint32_t epoch, ts_challenger *chal,
+                                uint8_t *commits_out, uint32_t *out_dev);
+/* Incremental form of ts_mmcs_commit (BFMmcs::commit, basic/src/mmcs/bf_mmcs.rs:23) for ONE matrix whose rows reach a rank
+ * as equal-width column blocks over time (the re-shard of a column-sharded LDE): the blocks are registered up front
+ * (borrowed, in column order), every window [block_begin, block_end) -- whole 64-byte Blake3 blocks of the row -- is
+ * absorbed as soon as its blocks have arrived, in order, and finish builds the tree.  The result equals ts_mmcs_commit
+ * over the same blocks.  Rows of at most 256 columns (one Blake3 chunk). */
+int ts_mmcs_commit_begin(ts_ctx *ctx, ts_matrix *const *blocks, size_t n_blocks, ts_tree **out);
+int ts_mmcs_commit_window(ts_ctx *ctx, ts_tree *tree, size_t block_begin, size_t block_end);
+int ts_mmcs_commit_finish(ts_ctx *ctx, ts_tree *tree, uint8_t *root_or_null);
 /* Chained commit-phase rounds of a ROW-SHARDED layer (fri/src/prover.rs:112-126 per round): nothing returns to the host
  * between rounds.  After whole digests have been observed the BfChallenger state is (root, previous squeeze), so one small
  * kernel per round combines the ranks' sub-roots into the layer root (top log2(n_sub) levels), advances the sponge

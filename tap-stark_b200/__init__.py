@@ -127,6 +127,11 @@ _SIGNATURES = {
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
     "ts_pcs_open": (C.c_int, [_vp, _vpp, C.c_size_t, _szp, _vp, C.c_uint, C.c_uint, C.c_uint, _vp, _vpp, _szp]),
     "ts_bytes_free": (None, [_vp]),
+    "ts_fri_mailbox_words": (C.c_int, []),
+    "ts_fri_commit_phase_sharded": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _vpp, C.c_uint32, _vp, _vp, _vp]),
+    "ts_mmcs_commit_begin": (C.c_int, [_vp, _vpp, C.c_size_t, _vpp]),
+    "ts_mmcs_commit_window": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t]),
+    "ts_mmcs_commit_finish": (C.c_int, [_vp, _vp, _vp]),
     "ts_taptree_commit": (C.c_int, [_vp, _vp, _vp, _szp, _vp, C.c_size_t, _u8p, _vpp]),
     "ts_taptree_leaf_indices": (C.c_int, [_vp, _vp, _vp]),
     "ts_taptree_level": (C.c_int, [_vp, _vp, C.c_uint, _vp]),

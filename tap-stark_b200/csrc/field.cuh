@@ -23,8 +23,15 @@ constexpr uint32_t MONTY_W = 0x37ffffe9u;    // 11 * R mod p  (x^4 = 11)
 constexpr uint32_t ROOT27 = 0x1a427a41u;     // canonical generator of the 2^27 subgroup
 
 TS_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// High word of a 32 x 32 product.  __umulhi compiles to IMAD.HI, which issues at HALF the rate of the other integer
+// multiply-adds on sm_100 (profiles/r01/int_pipes_b200.jsonl: 32 vs 63 lane-ops/clk/SM); a mul.wide whose low half is simply
+// not used stays an IMAD.WIDE (full rate) through ptxas.  -DTS_MULHI_WIDE selects it (A/B in profiles/r02/README.md).
 TS_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(TS_MULHI_WIDE)
+    unsigned long long t;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
+    return (uint32_t)(t >> 32);
+#elif defined(__CUDA_ARCH__)
     return __umulhi(a, b);
 #else
     return (uint32_t)(((uint64_t)a * b) >> 32);

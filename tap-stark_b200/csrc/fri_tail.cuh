@@ -144,4 +144,71 @@ __global__ void sponge_step_kernel(const uint32_t *sub_roots, int n_sub, uint32_
     }
 }
 
+// ---- sub-root exchange through peer memory (row-sharded layers, one process per GPU) ------------------------------------
+// Every rank owns a small MAILBOX that its peers map over CUDA IPC: roots[round][rank][8 words] and flags[round][rank].
+// After building the subtree of round r a rank PUBLISHES its sub-root into all G mailboxes (NVLink stores, then a
+// system-scope fence, then the flag = epoch); the sponge step of round r spins until all G flags of the round carry the
+// epoch and then runs the top of the tree and the sponge exactly as sponge_step_kernel does.  No NCCL call and no host
+// work separates the rounds: the collective is part of the kernels (the epoch, one per proving step, makes the mailbox
+// reusable without clearing it).
+constexpr int MAIL_ROUNDS = 32, MAIL_RANKS = 8;
+constexpr int MAIL_FLAGS_OFF = MAIL_ROUNDS * MAIL_RANKS * 8;           // in words
+constexpr int MAIL_WORDS = MAIL_FLAGS_OFF + MAIL_ROUNDS * MAIL_RANKS;  // 9216 words = 36 KiB
+struct Mailboxes {
+    uint32_t *box[MAIL_RANKS];
+};
+__global__ void publish_subroot_kernel(const uint32_t *sub_root, Mailboxes mb, int n_ranks, int my_rank, int round, uint32_t epoch) {
+    const int d = threadIdx.x;
+    if (d >= n_ranks || blockIdx.x != 0) return;
+    volatile uint32_t *dst = mb.box[d] + ((size_t)round * MAIL_RANKS + my_rank) * 8;
+    for (int k = 0; k < 8; k++) dst[k] = sub_root[k];
+#ifndef TS_EMULATE
+    __threadfence_system();
+#endif
+    volatile uint32_t *flag = mb.box[d] + MAIL_FLAGS_OFF + round * MAIL_RANKS + my_rank;
+    *flag = epoch;
+}
+__global__ void sponge_step_mailbox_kernel(const uint32_t *mailbox, int n_ranks, int round, uint32_t epoch, uint32_t *h_state,
+                                           uint32_t *root_out, uint32_t *half_beta_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const volatile uint32_t *flags = mailbox + MAIL_FLAGS_OFF + round * MAIL_RANKS;
+    // bounded wait (about two seconds): a peer that never publishes must not hang the GPU; the sponge then runs on whatever
+    // the mailbox holds and the transcript check of the caller fails loudly instead
+    uint32_t spins = 0;
+    for (int s = 0; s < n_ranks; s++) {
+        while (flags[s] != epoch && spins < 10000000u) {
+            spins++;
+#if !defined(TS_EMULATE) && defined(__CUDA_ARCH__)
+            __nanosleep(200);
+#endif
+        }
+    }
+#ifndef TS_EMULATE
+    __threadfence_system();
+#endif
+    uint32_t lvl[MAIL_RANKS][8];
+    const volatile uint32_t *roots = mailbox + (size_t)round * MAIL_RANKS * 8;
+    for (int i = 0; i < n_ranks; i++)
+        for (int k = 0; k < 8; k++) lvl[i][k] = roots[i * 8 + k];
+    for (int w = n_ranks; w > 1; w >>= 1)
+        for (int i = 0; i < w / 2; i++) {
+            uint32_t o[8];
+            b3::compress_pair(lvl[2 * i], lvl[2 * i + 1], b3::CHUNK_START | b3::CHUNK_END | b3::ROOT, o);
+            for (int k = 0; k < 8; k++) lvl[i][k] = o[k];
+        }
+    uint32_t hp[8], hn[8];
+    for (int k = 0; k < 8; k++) {
+        hp[k] = h_state[k];
+        root_out[k] = lvl[0][k];
+    }
+    b3::compress_pair(lvl[0], hp, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT, hn);
+    for (int k = 0; k < 8; k++) h_state[k] = hn[k];
+    for (int k = 0; k < 4; k++) {
+        uint32_t v = hn[7 - k];
+        v = v >= bb::P ? v - bb::P : v;
+        v = v >= bb::P ? v - bb::P : v;
+        half_beta_out[k] = bb::mmul(bb::to_monty(v), bb::MONTY_HALF);
+    }
+}
+
 }  // namespace ftail

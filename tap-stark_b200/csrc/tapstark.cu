@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cstdio>
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <functional>
@@ -1264,6 +1265,34 @@ int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t
 }  // namespace
 
 // ================================================================================================ C ABI
+// A pageable host matrix is page-locked for the duration of a *_host call: the column-chunk pipeline issues strided 2-D
+// copies, which the driver stages row by row out of pageable memory (measured 5.9 GB/s on a 2^22 x 256 trace, 0.73 s per
+// commit) but runs at the PCIe rate out of registered memory.  A caller that keeps its trace for several calls registers it
+// once itself (ts_host_register) and skips this cost.
+struct ScopedHostPin {
+    const void *p = nullptr;
+    ScopedHostPin(const void *host, size_t bytes) {
+#ifndef TS_EMULATE
+        if (!host || bytes < ((size_t)16 << 20) || getenv("TS_NO_AUTO_PIN")) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if (at.type != cudaMemoryTypeUnregistered) return;
+        if (cudaHostRegister(const_cast<void *>(host), bytes, cudaHostRegisterDefault) == cudaSuccess) p = host;
+        else cudaGetLastError();
+#else
+        (void)host, (void)bytes;
+#endif
+    }
+    ~ScopedHostPin() {
+#ifndef TS_EMULATE
+        if (p) cudaHostUnregister(const_cast<void *>(p));
+#endif
+    }
+};
+
 extern "C" {
 
 int ts_is_device_build(void) {
@@ -1615,6 +1644,7 @@ int ts_host_unregister(ts_ctx *c, const void *host) {
 int ts_coset_lde_batch_host(ts_ctx *c, const uint32_t *evals_host, size_t rows, size_t width, unsigned added_bits,
                             uint32_t shift_monty, int natural_order, uint32_t *out_host) {
     ts_matrix *in = nullptr, *o = nullptr;
+    ScopedHostPin pin_in(evals_host, rows * width * 4), pin_out(out_host, (rows << added_bits) * width * 4);
     int rc;
     if (!natural_order && log2_strict(rows) >= 0 && pipeline_eligible(rows, width)) {
         rc = new_matrix(c, rows << added_bits, width, &o);
@@ -2100,6 +2130,8 @@ int ts_pcs_commit_host(ts_ctx *c, const uint32_t *const *evals_host, const size_
                        const uint32_t *domain_shifts_monty, size_t n, unsigned log_blowup, int layout,
                        uint8_t root[32], ts_tree **out) {
     std::vector<ts_matrix *> ldes;
+    std::vector<std::unique_ptr<ScopedHostPin>> pins;
+    for (size_t i = 0; i < n; i++) pins.emplace_back(new ScopedHostPin(evals_host[i], rows[i] * widths[i] * 4));
     int rc = TS_OK;
     for (size_t i = 0; i < n && rc == TS_OK; i++) {
         const uint32_t dshift = h_from_monty(domain_shifts_monty[i]);
@@ -2490,6 +2522,7 @@ int ts_coset_lde_batch_scatter(ts_ctx *c, const ts_matrix *evals, unsigned added
 // CUDA IPC plumbing for the peer-mapped receive buffers (one process per GPU)
 int ts_device_malloc(ts_ctx *c, size_t bytes, void **out) {
     TS_CUDA(c, cudaMalloc(out, bytes));
+    TS_CUDA(c, cudaMemsetAsync(*out, 0, bytes, c->stream));  // zero-filled: mailboxes start with no flag set
     return TS_OK;
 }
 int ts_device_free(ts_ctx *c, void *p) {
@@ -2532,6 +2565,65 @@ int ts_ipc_close(ts_ctx *c, void *p) {
     TS_FAIL(c, TS_ERR_ARG, "ipc: not available in the emulated build");
 #endif
 }
+// ---- incremental commit of ONE matrix whose rows arrive as equal-width column blocks (row-sharded prover) ---------------
+// The row hash is sequential in the row, so blocks are absorbed in column order; between windows the chaining value of
+// every row is parked in the leaf-digest array (hash.cuh: hash_rows_fast_kernel, rows of at most one Blake3 chunk).
+int ts_mmcs_commit_begin(ts_ctx *c, ts_matrix *const *blocks, size_t n_blocks, ts_tree **out) {
+    if (!c || !blocks || !out || n_blocks == 0 || n_blocks > (size_t)b3::MAX_SEG) TS_FAIL(c, TS_ERR_ARG, "commit_begin: 1..32 column blocks");
+    const size_t rows = blocks[0]->rows, bw = blocks[0]->width;
+    if (log2_strict(rows) < 0 || bw < 4 || (bw & (bw - 1)) || bw * n_blocks > 256)
+        TS_FAIL(c, TS_ERR_ARG, "commit_begin: power-of-two rows, equal power-of-two block widths >= 4, at most 256 columns in total");
+    for (size_t i = 1; i < n_blocks; i++)
+        if (blocks[i]->rows != rows || blocks[i]->width != bw) TS_FAIL(c, TS_ERR_ARG, "commit_begin: blocks differ in shape");
+    ts_tree *t = new ts_tree;
+    t->ctx = c;
+    t->mats.assign(blocks, blocks + n_blocks);
+    t->own_mats = false;
+    t->layout = TS_LAYOUT_P3_INJECT;
+    t->digests = nullptr;
+    t->order.resize(n_blocks);
+    for (size_t i = 0; i < n_blocks; i++) t->order[i] = i;
+    t->hmax = rows;
+    t->lmax = (unsigned)log2_strict(rows);
+    size_t off = 0;
+    for (unsigned l = 0; l <= t->lmax; l++) {
+        t->layer_off.push_back(off);
+        off += rows >> l;
+    }
+    if (pool_alloc(c, (void **)&t->digests, off * 32) != cudaSuccess) {
+        ts_tree_free(t);
+        TS_FAIL(c, TS_ERR_CUDA, "commit_begin: digest allocation failed");
+    }
+    *out = t;
+    return TS_OK;
+}
+int ts_mmcs_commit_window(ts_ctx *c, ts_tree *t, size_t block_begin, size_t block_end) {
+    const size_t nb = t->mats.size(), bw = t->mats[0]->width;
+    if (block_begin >= block_end || block_end > nb || (block_begin * bw) % 16 || ((block_end * bw) % 16 && block_end != nb))
+        TS_FAIL(c, TS_ERR_ARG, "commit_window: windows must cover whole 64-byte blocks of the row");
+    b3::FastSegs fs;
+    for (int i = 0; i < b3::MAX_SEG; i++) fs.ptr[i] = i < (int)nb ? t->mats[i]->d : nullptr;
+    fs.n = (int)nb;
+    fs.seg_w = (uint32_t)bw;
+    fs.log_seg_w = 0;
+    while ((1u << fs.log_seg_w) < fs.seg_w) fs.log_seg_w++;
+    const size_t total = bw * nb;
+    KScope ks(c, TS_K_HASH_LEAVES);
+    auto kfn = b3::hash_rows_fast_kernel;
+    const size_t per_block = (size_t)b3::FAST_WARPS * 32;
+    TS_LAUNCH(kfn, (unsigned)((t->hmax + per_block - 1) / per_block), b3::FAST_WARPS * 32, (size_t)b3::FAST_WARPS * 512 * 4, c->stream, fs,
+              (uint32_t)total, t->hmax, 1, t->digests, (uint32_t)(block_begin * bw / 16), (uint32_t)((block_end * bw + 15) / 16));
+    return check_launch(c, "hash_rows_fast_kernel");
+}
+int ts_mmcs_commit_finish(ts_ctx *c, ts_tree *t, uint8_t *root_or_null) {
+    TS_TRY(build_tree(c, t, true));
+    if (root_or_null) {
+        TS_CUDA(c, cudaMemcpyAsync(root_or_null, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToHost, c->stream));
+        TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return TS_OK;
+}
+
 // ---- chained commit-phase rounds for a row-sharded layer (one process per GPU; collectives stay with the caller) -------
 static int xfer_ready(ts_ctx *c, int lane, bool after_main) {
     if (lane < 0 || lane >= ts_ctx::XFER_LANES) TS_FAIL(c, TS_ERR_ARG, "copy: lane must be 0..7");
@@ -2627,6 +2719,67 @@ int ts_fri_chain_end(ts_ctx *c, uint32_t *chain_dev, ts_challenger *chal, size_t
         ts_challenger_sample_ext(chal, beta);
     }
     return TS_OK;
+}
+int ts_fri_mailbox_words(void) { return ftail::MAIL_WORDS; }
+// All sharded commit-phase rounds of one step in one call: per round leaf hash + subtree, publish the sub-root into every
+// rank's mailbox, sponge step once all sub-roots of the round have arrived, fold with the beta it leaves on the device.
+int ts_fri_commit_phase_sharded(ts_ctx *c, const uint32_t *cur_dev, size_t len_global, size_t rank, size_t world, size_t n_rounds,
+                                uint32_t *const *mailboxes, uint32_t epoch, ts_challenger *chal, uint8_t *commits_out,
+                                uint32_t *out_dev) {
+    if (!c || !cur_dev || !mailboxes || !chal || !out_dev) TS_FAIL(c, TS_ERR_ARG, "fri sharded: null argument");
+    if (world < 2 || world > (size_t)ftail::MAIL_RANKS || (world & (world - 1)) || rank >= world || n_rounds == 0 || n_rounds > (size_t)ftail::MAIL_ROUNDS)
+        TS_FAIL(c, TS_ERR_ARG, "fri sharded: 2..8 ranks (a power of two), 1..32 rounds");
+    if (log2_strict(len_global) < 0 || (len_global >> n_rounds) / world < 1 || ((len_global >> n_rounds) / world) * world != (len_global >> n_rounds))
+        TS_FAIL(c, TS_ERR_ARG, "fri sharded: the layers must stay divisible among the ranks");
+    uint32_t *chain = nullptr;
+    TS_TRY(ts_fri_chain_begin(c, chal, n_rounds, &chain));
+    ftail::Mailboxes mb;
+    for (size_t i = 0; i < (size_t)ftail::MAIL_RANKS; i++) mb.box[i] = i < world ? mailboxes[i] : nullptr;
+    uint32_t *cur = const_cast<uint32_t *>(cur_dev);
+    bool cur_owned = false;
+    size_t len_g = len_global, local = len_global / world;
+    int rc = TS_OK;
+    for (size_t r = 0; r < n_rounds && rc == TS_OK; r++) {
+        const size_t h_g = len_g / 2, h_l = local / 2;
+        ts_matrix *leaves = new ts_matrix{c, cur, h_l, 8, cur_owned};
+        ts_tree *tree = nullptr;
+        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, nullptr, &tree, false);
+        if (rc != TS_OK) {
+            ts_matrix_free(leaves);
+            cur = nullptr;
+            break;
+        }
+        {
+            KScope ks(c, TS_K_TREE);
+            auto kfn = ftail::publish_subroot_kernel;
+            TS_LAUNCH(kfn, 1, 32, 0, c->stream, (const uint32_t *)(tree->digests + tree->layer_off[tree->lmax] * 8), mb, (int)world, (int)rank, (int)r,
+                      epoch);
+            rc = check_launch(c, "publish_subroot_kernel");
+        }
+        if (rc == TS_OK) {
+            KScope ks(c, TS_K_TREE);
+            auto kfn = ftail::sponge_step_mailbox_kernel;
+            TS_LAUNCH(kfn, 1, 32, 0, c->stream, (const uint32_t *)mailboxes[rank], (int)world, (int)r, epoch, chain, chain + 12 + 8 * r, chain + 8);
+            rc = check_launch(c, "sponge_step_mailbox_kernel");
+        }
+        uint32_t *nf = out_dev;
+        if (rc == TS_OK && r + 1 < n_rounds && pool_alloc(c, (void **)&nf, h_l * 16) != cudaSuccess) {
+            c->err = "fri sharded: layer allocation failed";
+            rc = TS_ERR_CUDA;
+        }
+        if (rc == TS_OK) rc = fold_ext_launch(c, cur, nf, nullptr, log2_strict(h_g), nullptr, rank * h_l, h_l, chain + 8);
+        ts_tree_free(tree);  // releases the layer it owns (stream-ordered pool)
+        cur = nf;
+        cur_owned = r + 1 < n_rounds;
+        len_g = h_g;
+        local = h_l;
+    }
+    if (rc != TS_OK) {
+        if (cur_owned && cur) pool_release(c, cur);
+        ts_fri_chain_end(c, chain, nullptr, 0, nullptr);
+        return rc;
+    }
+    return ts_fri_chain_end(c, chain, chal, n_rounds, commits_out);
 }
 int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev) {

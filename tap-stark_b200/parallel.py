@@ -129,6 +129,40 @@ class ShardedProver:
         cache[key] = plan if int(flag.item()) == 1 else None
         return cache[key]
 
+    def _mailbox_setup(self):
+        """Peer-mapped mailboxes of the sharded FRI rounds (ts_fri_commit_phase_sharded): allocated and exchanged once.
+        Returns the pointer table (rank order) or None when unavailable (CPU/gloo, IPC refused, TS_NO_MAILBOX): the caller
+        then exchanges sub-roots with a 32-byte all-gather per round.  Collective on first use."""
+        import os
+
+        if hasattr(self, "_mail"):
+            return self._mail
+        torch, dist, ctx, L, G, r = self.torch, self.dist, self.ctx, self.ctx._L, self.world, self.rank
+        ok = self.device.type == "cuda" and dist.get_backend() == "nccl" and G <= 8 and os.environ.get("TS_NO_MAILBOX") is None
+        own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        if ok:
+            ok = L.ts_device_malloc(ctx._h, L.ts_fri_mailbox_words() * 4, C.byref(own)) == 0 and L.ts_ipc_get_handle(ctx._h, own, handle) == 0
+        gathered = [None] * G
+        dist.all_gather_object(gathered, bytes(handle) if ok else None)
+        ok = ok and all(g is not None for g in gathered)
+        table = (C.c_void_p * G)()
+        if ok:
+            for d in range(G):
+                if d == r:
+                    table[d] = own.value
+                    continue
+                q_ = C.c_void_p()
+                if L.ts_ipc_open(ctx._h, C.c_char_p(gathered[d]), C.byref(q_)) != 0:
+                    ok = False
+                    break
+                table[d] = q_.value
+                self.__dict__.setdefault("_p2p_mapped", []).append(q_.value)
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # everyone or no one; also orders every mailbox's zero-fill before its first use
+        self._mail = table if int(flag.item()) == 1 else None
+        self._mail_own = own.value if ok else None
+        return self._mail
+
     def reshard_mode(self) -> str:
         """How LDE rows travel to their owners.  TS_RESHARD = ce | nccl | fused (TS_P2P=1 is the round-1 spelling of fused)."""
         import os
@@ -148,6 +182,9 @@ class ShardedProver:
                 L.ts_device_free(ctx._h, C.c_void_p(own_base))
         for p_ in self.__dict__.pop("_p2p_mapped", []):
             L.ts_ipc_close(ctx._h, C.c_void_p(p_))
+        if self.__dict__.pop("_mail_own", None):
+            pass  # the mailbox (36 KiB) lives as long as the process: peers may still have it mapped
+        self.__dict__.pop("_mail", None)
 
     def combine_roots(self, data) -> bytes:
         """all-gather the G sub-roots (device to device: the sub-root never visits the host on its own) and hash the
@@ -187,10 +224,23 @@ class ShardedProver:
             c *= 2
         return c if self.world > 1 else 1
 
+    def owned_columns(self, width_total: int):
+        """Global column indices of this rank's shard, in local order.  Ownership is CHUNK-MAJOR: the w columns are cut
+        into C chunks of G*wc columns and rank r owns columns [r*wc, (r+1)*wc) of every chunk.  After the re-shard of chunk c
+        a rank therefore holds the CONTIGUOUS global columns [c*G*wc, (c+1)*G*wc) of its rows, i.e. whole 64-byte blocks of
+        the row hash, which is absorbed while the next chunk is still being transformed and exchanged."""
+        G, r = self.world, self.rank
+        wl = width_total // G
+        C_ = self._chunks(wl)
+        wc = wl // C_
+        return [c * G * wc + r * wc + j for c in range(C_) for j in range(wc)]
+
     def host_panels(self, trace_t):
         """Pinned host copy of this rank's shard as column panels (one contiguous [n, wc] tensor per chunk): the
         layout a column-sharded host prover hands over, so that panel c+1 is copied while panel c is transformed."""
         torch = self.torch
+        if isinstance(trace_t, (list, tuple)):
+            trace_t = torch.cat(list(trace_t), dim=1)
         n, wl = trace_t.shape
         C_ = self._chunks(wl)
         wc = wl // C_
@@ -213,6 +263,8 @@ class ShardedProver:
             n, wl = host_full.shape[0], host_full.shape[1] // G
         elif host_panels is not None:
             n, wl = host_panels[0].shape[0], sum(p_.shape[1] for p_ in host_panels)
+        elif isinstance(trace_t, (list, tuple)):
+            n, wl = trace_t[0].shape[0], sum(t_.shape[1] for t_ in trace_t)
         else:
             n, wl = trace_t.shape
         N = n << b
@@ -220,8 +272,9 @@ class ShardedProver:
         C_ = self._chunks(wl)
         wc = wl // C_
         gen = int(ts.to_monty(ts.GENERATOR))
+        import os
+
         recv, works, keep = [], [], []
-        own_rows = []  # copy-engine re-shard: chunk c's LDE, whose rows [r*Nl, (r+1)*Nl) stay in place
         staged = []
         marks = [self._mark()]
         if host_full is not None:
@@ -232,7 +285,7 @@ class ShardedProver:
                 staged.append(torch.empty((n, wc), dtype=torch.int32, device=self.device))
 
             def issue_h2d(c):
-                src = host_full.data_ptr() + (r * wl + c * wc) * 4
+                src = host_full.data_ptr() + (c * G * wc + r * wc) * 4  # chunk-major ownership (owned_columns)
                 ctx.check(L.ts_copy2d_async(ctx._h, 0, C.c_void_p(staged[c].data_ptr()), wc * 4, C.c_void_p(src), W * 4, wc * 4, n,
                                             1 if c == 0 else 0), "copy2d_async")
 
@@ -254,6 +307,45 @@ class ShardedProver:
                     staged.append((d_, e_))
         mode = self.reshard_mode()
         plan = self._p2p_setup(N, wc, C_) if (G > 1 and n >= 1 << 18 and wc % 4 == 0) else None
+        ce = plan is not None and mode != "fused"
+        # copy-engine re-shard: every chunk's LDE stays allocated (its own row range is hashed in place) and the row hash is
+        # INCREMENTAL: chunk c-1's columns are absorbed while chunk c is transformed and exchanged
+        incremental = ce and (G * wc) % 16 == 0 and G * C_ <= 32 and G * C_ * wc <= 256 and os.environ.get("TS_NO_INC_HASH") is None
+        blk = Nl * wc * 4
+        lde_ts = [torch.empty((N, wc), dtype=torch.int32, device=self.device) for _ in range(C_)] if ce else []
+
+        def chunk_blocks(c):  # global column order inside a chunk: rank-major
+            out = []
+            for s_ in range(G):
+                if ce and s_ == r:
+                    out.append(ts.DeviceMatrix.wrap_device(ctx, lde_ts[c].data_ptr() + r * blk, Nl, wc, keepalive=lde_ts[c]))
+                elif plan is not None:
+                    out.append(ts.DeviceMatrix.wrap_device(ctx, plan[c][0] + s_ * blk, Nl, wc))
+                else:
+                    out.append(self._wrap(recv[c][s_], Nl, wc))
+            return out
+
+        tree = None
+        if incremental:
+            blocks = [b_ for c in range(C_) for b_ in chunk_blocks(c)]
+            arr = (C.c_void_p * len(blocks))(*[b_._h for b_ in blocks])
+            th = C.c_void_p()
+            ctx.check(L.ts_mmcs_commit_begin(ctx._h, arr, len(blocks), C.byref(th)), "mmcs_commit_begin")
+            tree = ts.ProverData(ctx, th, blocks, False)
+        if not hasattr(self, "_p2p_flag") and plan is not None:
+            self._p2p_flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+        n_lanes = min(self.peer_lanes, 2)
+        lag = max(1, min(2, int(os.environ.get("TS_HASH_LAG", "2"))))  # a chunk is hashed `lag` LDEs after its own
+
+        def lanes_of(c):  # three rotating sets of copy queues: "chunk c has landed" is awaited without waiting for c+1, c+2
+            return [1 + (c % 3) * 2 + k for k in range(n_lanes)]
+
+        def chunk_landed(c):
+            """this rank's copies of chunk c are done and, after the collective, so are everyone's into this rank"""
+            for lane in lanes_of(c):
+                ctx.check(L.ts_copy_join(ctx._h, lane), "copy_join")
+            dist.all_reduce(self._p2p_flag)
+
         for c in range(C_):
             if host_full is not None:
                 src_t = staged[c]
@@ -262,6 +354,8 @@ class ShardedProver:
             elif host_panels is not None:
                 src_t, ev_ = staged[c]
                 torch.cuda.current_stream().wait_event(ev_)
+            elif isinstance(trace_t, (list, tuple)):
+                src_t = trace_t[c]
             else:
                 src_t = trace_t if C_ == 1 else trace_t[:, c * wc : (c + 1) * wc].contiguous()
             ev = self._wrap(src_t, n, wc)
@@ -272,31 +366,34 @@ class ShardedProver:
                 if host_full is not None and c + 1 < C_:
                     ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")
                 continue
-            lde_t = torch.empty((N, wc), dtype=torch.int32, device=self.device)
+            lde_t = lde_ts[c] if ce else torch.empty((N, wc), dtype=torch.int32, device=self.device)
             lde = self._wrap(lde_t, N, wc)
             ctx.check(L.ts_coset_lde_batch_into(ctx._h, ev._h, b, gen, lde._h), "coset_lde_batch_into")
             if host_full is not None and c + 1 < C_:
                 ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")  # the next window must have landed before its LDE starts
-            if plan is not None:
-                # copy-engine re-shard (transfer lane 1): this rank's rows [d*Nl, (d+1)*Nl) of the chunk go to rank d's receive
-                # buffer over NVLink while the SMs run the next chunk's LDE; peers are visited starting after this rank so
-                # that no receiver is everybody's first target
-                blk = Nl * wc * 4
-                n_lanes = self.peer_lanes
-                pieces = max(1, -(-n_lanes // (G - 1)))  # keep n_lanes copy queues busy whatever the peer count
+            if ce:
+                # this rank's rows [d*Nl, (d+1)*Nl) of the chunk go to rank d's receive buffer over NVLink (copy engines) while
+                # the SMs run the next chunk's LDE; peers are visited starting after this rank so that no receiver is
+                # everybody's first target; this rank's own rows stay where they are
+                lanes = lanes_of(c)
+                pieces = max(1, -(-len(lanes) // (G - 1)))  # keep every queue busy whatever the peer count
                 issued = set()
                 q = 0
-                for k in range(G - 1):  # this rank's own rows are hashed where they are: no self copy
+                for k in range(G - 1):
                     d = (r + 1 + k) % G
                     for pc_ in range(pieces):
-                        lane = 1 + q % n_lanes
+                        lane = lanes[q % len(lanes)]
                         q += 1
-                        lo, hi = blk * pc_ // pieces // 16 * 16, blk * (pc_ + 1) // pieces // 16 * 16 if pc_ + 1 < pieces else blk
+                        lo = blk * pc_ // pieces // 16 * 16
+                        hi = blk * (pc_ + 1) // pieces // 16 * 16 if pc_ + 1 < pieces else blk
                         ctx.check(L.ts_copy_async(ctx._h, lane, C.c_void_p(plan[c][1][d] + lo), C.c_void_p(lde_t.data_ptr() + d * blk + lo),
                                                   hi - lo, 0 if lane in issued else 1), "copy_async")
                         issued.add(lane)
-                own_rows.append(lde_t)
-                keep.append((lde_t, src_t))
+                keep.append(src_t)
+                if incremental and c >= lag:
+                    # the exchange of chunk c-lag has had `lag` LDEs (and the windows between them) to finish
+                    chunk_landed(c - lag)
+                    ctx.check(L.ts_mmcs_commit_window(ctx._h, tree._h, (c - lag) * G, (c - lag + 1) * G), "mmcs_commit_window")
                 continue
             recv_t = torch.empty((G, Nl, wc), dtype=torch.int32, device=self.device)
             send_list, recv_list = list(lde_t.view(G, Nl, wc).unbind(0)), list(recv_t.unbind(0))
@@ -309,28 +406,27 @@ class ShardedProver:
         marks_detail = [self._mark()]  # all LDE launches queued behind this point
         for w_ in works:
             w_.wait()
-        if plan is not None:
-            if mode != "fused":
-                for lane in range(1, 1 + self.peer_lanes):
+        if incremental:
+            for c in range(max(C_ - lag, 0), C_):
+                chunk_landed(c)
+                if c == C_ - 1:
+                    marks.append(self._mark())  # LDE + re-shard done (all but the last hash windows already ran inside it)
+                ctx.check(L.ts_mmcs_commit_window(ctx._h, tree._h, c * G, (c + 1) * G), "mmcs_commit_window")
+            ctx.check(L.ts_mmcs_commit_finish(ctx._h, tree._h, None), "mmcs_commit_finish")
+            data = tree
+        else:
+            if ce:
+                for lane in range(1, 7):
                     ctx.check(L.ts_copy_join(ctx._h, lane), "copy_join")
-            # every rank's stores into my buffers are complete once all ranks have passed this point in stream order
-            if not hasattr(self, "_p2p_flag"):
-                self._p2p_flag = torch.zeros(1, device=self.device, dtype=torch.int32)
-            dist.all_reduce(self._p2p_flag)
-        if not own_rows:
-            keep = None
-        marks.append(self._mark())  # LDE + re-shard done
-        # global column order: rank-major, then chunk
-        blocks = []
-        for s_ in range(G):
-            for c in range(C_):
-                if plan is not None and own_rows and s_ == r:
-                    blocks.append(ts.DeviceMatrix.wrap_device(ctx, own_rows[c].data_ptr() + r * Nl * wc * 4, Nl, wc, keepalive=own_rows[c]))
-                elif plan is not None:
-                    blocks.append(ts.DeviceMatrix.wrap_device(ctx, plan[c][0] + s_ * Nl * wc * 4, Nl, wc))
-                else:
-                    blocks.append(self._wrap(recv[c][s_], Nl, wc))
-        _, data = self.mmcs.commit(blocks, host_root=False)
+            if plan is not None:
+                # every rank's stores into my buffers are complete once all ranks have passed this point in stream order
+                dist.all_reduce(self._p2p_flag)
+            if not ce:
+                keep = None
+            marks.append(self._mark())  # LDE + re-shard done
+            # global column order: chunk-major, then rank (owned_columns)
+            blocks = [b_ for c in range(C_) for b_ in chunk_blocks(c)]
+            _, data = self.mmcs.commit(blocks, host_root=False)
         root = self.combine_roots(data)
         marks.append(self._mark())  # leaf hashes, sub-tree, sub-root all-gather
         ch = ts.BfChallenger()
@@ -346,7 +442,7 @@ class ShardedProver:
         ctx.check(L.ts_dot_ext_powers_blocks(ctx._h, arr, len(blocks), ap, fri._h), "dot_ext_powers_blocks")
         L.ts_matrix_free(ap)
         data.free()
-        blocks = own_rows = keep = None
+        blocks = lde_ts = keep = tree = None
         marks.append(self._mark())  # alpha reduction
         commits, final = self._fri_commit_phase(fri_t, N, ch)
         marks.append(self._mark())  # FRI commit phase
@@ -388,6 +484,16 @@ class ShardedProver:
         lg, lc = len_g, local
         while lg > blowup and lg > self.REPLICATE_BELOW and (lc // 2) >= 256 and (lc // 2) * G == lg // 2:
             sharded, lg, lc = sharded + 1, lg // 2, lc // 2
+        mail = self._mailbox_setup() if sharded else None
+        if mail is not None:
+            # every sharded round in ONE library call; the sub-roots travel through peer-mapped mailboxes inside the kernels
+            self._epoch = getattr(self, "_epoch", 0) + 1
+            out_t = torch.empty((local >> sharded, 4), dtype=torch.int32, device=self.device)
+            cbuf = np.zeros((sharded, 32), dtype=np.uint8)
+            ctx.check(L.ts_fri_commit_phase_sharded(ctx._h, C.c_void_p(cur_t.data_ptr()), len_g, r, G, sharded, mail, self._epoch, ch._h,
+                                                    cbuf.ctypes.data_as(C.c_void_p), C.c_void_p(out_t.data_ptr())), "fri_commit_phase_sharded")
+            commits += [cbuf[i].tobytes() for i in range(sharded)]
+            cur_t, len_g, local, sharded = out_t, len_g >> sharded, local >> sharded, 0
         chain = C.c_void_p()
         if sharded:
             ctx.check(L.ts_fri_chain_begin(ctx._h, ch._h, sharded, C.byref(chain)), "fri_chain_begin")
@@ -444,10 +550,14 @@ class ShardedRunner:
         dev = torch.device("cuda", torch.cuda.current_device())
         # this rank's columns [rank*wl, (rank+1)*wl) of the ONE synthetic trace every N works on (element
         # (r, c) = SplitMix64((seed << 40) + r*width + c) mod p), so root and final polynomial are the 1-GPU ones
-        self.trace_t = torch.empty((self.n, self.wl), dtype=torch.int32, device="cuda")
-        ctx.check(ctx._L.ts_fill_splitmix(ctx._h, self.trace_t.data_ptr(), self.n, self.wl, seed, rank * self.wl, width, 1),
-                  "fill_splitmix")
         self.prover = ShardedProver(ts, ctx, rank, world, log_blowup, dev)
+        C_ = self.prover._chunks(self.wl)
+        wc = self.wl // C_
+        self.trace_t = []  # one contiguous [n, wc] tensor per column chunk (ShardedProver.owned_columns: chunk-major ownership)
+        for c in range(C_):
+            t = torch.empty((self.n, wc), dtype=torch.int32, device="cuda")
+            ctx.check(ctx._L.ts_fill_splitmix(ctx._h, t.data_ptr(), self.n, wc, seed, c * world * wc + rank * wc, width, 1), "fill_splitmix")
+            self.trace_t.append(t)
         self.parallelism = (f"{world} GPUs: LDE column-sharded ({self.wl} cols/GPU), NCCL all-to-all re-shard by rows, "
                             f"row-sharded Blake3 subtrees + FRI folding, 32-byte sub-root all-gathers")
         self.h2d_bytes = self.n * self.wl * 4
@@ -464,7 +574,7 @@ class ShardedRunner:
         n, W = self.n, self.wl * self.world
         full = torch.empty((n, W), dtype=torch.int32, pin_memory=True)
         tmp = torch.empty((n, self.wl), dtype=torch.int32, device="cuda")
-        for s_ in range(self.world):  # the same generator every rank uses for its resident shard
+        for s_ in range(self.world):  # the same generator every rank uses for its resident shard, 1/G of the columns at a time
             self.ctx.check(self.ctx._L.ts_fill_splitmix(self.ctx._h, tmp.data_ptr(), n, self.wl, self.seed, s_ * self.wl, W, 1),
                            "fill_splitmix")
             torch.cuda.current_stream().synchronize()

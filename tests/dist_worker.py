@@ -29,10 +29,9 @@ def main():
 
     ctx = ts.Context(0)
     trace = orc.splitmix_matrix(5, 1 << log_n, width)  # canonical, full trace (every rank derives its shard)
-    wl = width // world
-    shard = ts.to_monty(np.ascontiguousarray(trace[:, rank * wl : (rank + 1) * wl]))
-    shard_t = torch.from_numpy(shard.view(np.int32).copy())
     prover = ShardedProver(ts, ctx, rank, world, b, torch.device("cpu"))
+    shard = ts.to_monty(np.ascontiguousarray(trace[:, prover.owned_columns(width)]))  # chunk-major column ownership
+    shard_t = torch.from_numpy(shard.view(np.int32).copy())
     prover.REPLICATE_BELOW = int(os.environ.get("TS_REPLICATE_BELOW", "64"))  # exercise the row-sharded FRI rounds
     res = prover.commit_and_fri(shard_t)
     res["root"] = res["root"].hex()

@@ -30,10 +30,9 @@ def main():
     with torch.cuda.stream(stream):
         ctx = ts.Context(local, stream=stream.cuda_stream)
         trace = orc.splitmix_matrix(5, 1 << log_n, width)  # canonical, full trace (every rank derives its shard)
-        wl = width // world
-        shard = ts.to_monty(np.ascontiguousarray(trace[:, rank * wl : (rank + 1) * wl]))
-        shard_t = torch.from_numpy(shard.view(np.int32).copy()).cuda()
         prover = ShardedProver(ts, ctx, rank, world, b, torch.device("cuda", local))
+        shard = ts.to_monty(np.ascontiguousarray(trace[:, prover.owned_columns(width)]))  # chunk-major column ownership
+        shard_t = torch.from_numpy(shard.view(np.int32).copy()).cuda()
         prover.REPLICATE_BELOW = int(os.environ.get("TS_REPLICATE_BELOW", str(1 << 12)))
         out = {}
         full_host = torch.from_numpy(ts.to_monty(trace).view(np.int32).copy()).pin_memory()

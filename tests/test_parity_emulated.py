@@ -1,6 +1,7 @@
 """Kernel-source parity WITHOUT a GPU: tap-stark_b200/csrc compiled by g++ against the SIMT emulator in
 tests/emul (test-only; see tests/emul/cuda_emul.h) and compared bit-exactly with the oracle.  These are the
 same cases the GPU module runs on the real library, at emulator-friendly sizes."""
+import numpy as np
 import pytest
 
 import parity_cases as pc
@@ -145,6 +146,29 @@ def test_commit_phase(ts, ctx, orc):
     pc.check_commit_phase(ts, ctx, orc, [6], 2)
     pc.check_commit_phase(ts, ctx, orc, [7, 5, 4], 1)
     pc.check_commit_phase_rejects_high_degree(ts, ctx)
+
+
+@pytest.mark.parametrize("rows,bw,nb,windows", [(64, 8, 4, [(0, 2), (2, 4)]), (256, 16, 8, [(0, 1), (1, 5), (5, 8)]), (32, 4, 8, [(0, 4), (4, 8)])])
+def test_mmcs_incremental_commit(ts, ctx, orc, rows, bw, nb, windows):
+    """ts_mmcs_commit_begin / _window / _finish: the row hash absorbed block window by block window (the row-sharded
+    prover hashes a chunk's columns while the next chunk is still in flight) gives the root of the one-shot commit."""
+    import ctypes as C
+
+    m = pc.rand_mat(77, rows, bw * nb)
+    blocks = [ts.DeviceMatrix.from_canonical(ctx, np.ascontiguousarray(m[:, i * bw : (i + 1) * bw])) for i in range(nb)]
+    want = orc.mmcs_commit([m]).root
+    root, data = ts.Blake3MerkleMmcs(ctx).commit(blocks)
+    assert root == want
+    arr = (C.c_void_p * nb)(*[b._h for b in blocks])
+    th = C.c_void_p()
+    ctx.check(ctx._L.ts_mmcs_commit_begin(ctx._h, arr, nb, C.byref(th)), "commit_begin")
+    for b0, b1 in windows:
+        ctx.check(ctx._L.ts_mmcs_commit_window(ctx._h, th, b0, b1), "commit_window")
+    got = (C.c_uint8 * 32)()
+    ctx.check(ctx._L.ts_mmcs_commit_finish(ctx._h, th, got), "commit_finish")
+    assert bytes(got) == want
+    assert ctx._L.ts_mmcs_commit_window(ctx._h, th, 1, 1) != 0  # empty window
+    ctx._L.ts_tree_free(th)
 
 
 @pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {}])
