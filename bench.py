@@ -360,10 +360,10 @@ def run_b200(a):
             roof = {"kernel": dom, "bound": "hbm", "achieved": per_launch_bytes / per_launch_s / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": per_launch_bytes / per_launch_s / 1e9 / peak, "traffic": traffic,
                     "alg_bytes_per_launch": per_launch_bytes, "avg_launch_ms": per_launch_s * 1e3, "peak_source": peak_src,
-                    "note": "rank 0's kernels; algorithmic bytes = compulsory I/O of that kernel class (DESIGN.md 4). The NTT kernels "
-                            "are INT32-issue/latency bound, not HBM bound: with every CTA on one L2-resident tile they take the same "
-                            "time (profiles/r01/README.md, 'compute-only' experiment); Blake3 leaves run the ALU pipe at 74 % and "
-                            "issue on 73 % of cycles (profiles/r01/v11_ncu_full.md)"}
+                    "note": "rank 0's kernels; algorithmic bytes = compulsory I/O of that kernel class (DESIGN.md 4): every digit pass "
+                            "reads and writes its whole matrix once. The NTT kernels are INT32-issue bound, not HBM bound (both integer "
+                            "pipes ~57 % busy, issue slots 61 %, profiles/r02/a_ncu_v4.md); `lde_stage` below is the whole LDE against the "
+                            "5 B per output element of SURVEY 8(d); Blake3 leaves run the ALU pipe at 74 % (profiles/r01/v11_ncu_full.md)"}
         lde_ms = sum(per_kind.get(k, {}).get("ms_per_step", 0) for k in ("ntt_pass", "lde_mid"))
         # INT32 view of the LDE (the bound that actually applies): butterflies per second of this rank's
         # shard against the butterfly issue rate measured on a B200 by profiles/tools/int_pipes.cu

@@ -240,7 +240,7 @@ void ts_bytes_free(uint8_t *bytes);
  * x_k = canonical value of word push_word[k-1] of row i of `leaf_rows` (Montgomery on the device; for extension elements
  * the host lists the limbs in the reversed order of tcs/mod.rs:214).  segs = the n_push + 1 segments concatenated,
  * seg_offsets = n_push + 2 offsets.  The locking-script bytes themselves come from the external `bitcomm` crate (PARITY
- * UNPINNED; oracle/taptree.py restates them from the in-tree twin scripts/src/bit_comm/*).  The reference repeats this
+ * UNPINNED; oracle/taptree.py restates them from the in-tree twin under scripts/src/bit_comm).  The reference repeats this
  * commit num_queries times with fresh bit-commitments (tcs/mod.rs:284-292): call once per template.
  * Outputs: root (32 bytes, as TapNodeHash serialises), the tree handle; leaf_indices[m] = position of Merkle leaf m among
  * the TapTree's leaves (CompleteTaptree's reverse_idx_dict); ts_taptree_level downloads one level (0 = leaf hashes). */

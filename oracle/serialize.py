@@ -67,3 +67,12 @@ def encode_fri_proof(proof) -> bytes:
 
 def encode_opening(opened, proof) -> bytes:
     return encode_opened_values(opened) + encode_fri_proof(proof)
+
+
+def encode_stark_proof(proof) -> bytes:
+    """uni-stark/src/proof.rs:19-37, field by field in declaration order."""
+    out = bytes(proof.commitments.trace) + bytes(proof.commitments.quotient_chunks)
+    ov = proof.opened_values
+    out += _ef_vec(ov.trace_local) + _ef_vec(ov.trace_next) + _vec(ov.quotient_chunks, _ef_vec)
+    out += encode_fri_proof(proof.opening_proof)
+    return out + varint(proof.degree_bits)

@@ -46,8 +46,9 @@ class Reader:
         return self.o == len(self.b)
 
 
-def decode_opening(data: bytes):
-    """bytes of ts_pcs_open -> (opened_values[round][matrix][point] -> (width, 4) array, FriProof)."""
+def decode_opening(data: bytes, want_split: bool = False):
+    """bytes of ts_pcs_open -> (opened_values[round][matrix][point] -> (width, 4) array, FriProof).
+    want_split: also return the byte offset at which the FriProof starts (uni_stark::Proof embeds it as opening_proof)."""
     from . import BatchOpening, BfQueryProof, FriProof
 
     r = Reader(data)
@@ -61,10 +62,11 @@ def decode_opening(data: bytes):
                 mat.append(np.stack([r.ef() for _ in range(w)]) if w else np.zeros((0, 4), dtype=np.uint32))
             rnd.append(mat)
         opened.append(rnd)
+    split = r.o
     proof = decode_fri_proof(r)
     if not r.done():
         raise ValueError("trailing bytes after the opening proof")
-    return opened, proof
+    return (opened, proof, split) if want_split else (opened, proof)
 
 
 def decode_fri_proof(r: Reader):
@@ -90,3 +92,28 @@ def decode_fri_proof(r: Reader):
     final_poly = r.ef()
     pow_witness = r.varint()
     return FriProof(commits, queries, final_poly, pow_witness)
+
+
+def varint(v: int) -> bytes:
+    out = bytearray()
+    v = int(v)
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _ef_vec(a) -> bytes:
+    a = np.asarray(a, dtype=np.uint32).reshape(-1, 4)
+    return varint(a.shape[0]) + b"".join(varint(int(x)) for x in a.reshape(-1))
+
+
+def encode_stark_proof(commit_trace: bytes, commit_quotient: bytes, trace_local, trace_next, quotient_chunks,
+                       fri_proof_bytes: bytes, degree_bits: int) -> bytes:
+    """postcard of uni_stark::Proof (uni-stark/src/proof.rs:19-37): commitments { trace, quotient_chunks }, opened_values
+    { trace_local, trace_next, quotient_chunks }, opening_proof (the FriProof bytes of ts_pcs_open, verbatim), degree_bits."""
+    out = bytes(commit_trace) + bytes(commit_quotient)
+    out += _ef_vec(trace_local) + _ef_vec(trace_next)
+    out += varint(len(quotient_chunks)) + b"".join(_ef_vec(c) for c in quotient_chunks)
+    return out + fri_proof_bytes + varint(degree_bits)

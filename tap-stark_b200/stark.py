@@ -209,6 +209,16 @@ class Proof:  # uni-stark/src/proof.rs:19-25
     opened_values: OpenedValues
     opening_proof: FriProof
     degree_bits: int
+    opening_proof_bytes: bytes = b""  # the FriProof exactly as ts_pcs_open serialised it
+
+    def to_bytes(self) -> bytes:
+        """postcard of the whole proof (the reference's one serialisation call is postcard::to_allocvec(&proof),
+        commented out at uni-stark/tests/mul_air.rs:133)."""
+        from . import proofio
+
+        return proofio.encode_stark_proof(self.commitments.trace, self.commitments.quotient_chunks, self.opened_values.trace_local,
+                                          self.opened_values.trace_next, self.opened_values.quotient_chunks,
+                                          self.opening_proof_bytes, self.degree_bits)
 
 
 def quotient_values(pcs: TwoAdicFriPcs, trace_data, air, public_values: Sequence[int], log_n: int, log_quotient_degree: int,
@@ -248,6 +258,10 @@ def prove(pcs: TwoAdicFriPcs, air, challenger: BfChallenger, trace: np.ndarray, 
     zeta = [int(x) for x in challenger.sample()]  # :92
     g_n = two_adic_generator(log_degree)
     zeta_next = [c * g_n % P for c in zeta]  # trace_domain.next_point(zeta)
-    opened, opening_proof = pcs.open([(trace_data, [[zeta, zeta_next]]), (quotient_data, [[zeta]] * qd)], challenger)  # :95-105
+    # :95-105 -- Pcs::open through ONE C-ABI call (ts_pcs_open); the bytes decode into the proof objects
+    from . import proofio
+
+    blob = pcs.open_bytes([(trace_data, [[zeta, zeta_next]]), (quotient_data, [[zeta]] * qd)], challenger)
+    opened, opening_proof, split = proofio.decode_opening(blob, want_split=True)
     ov = OpenedValues(opened[0][0][0], opened[0][0][1], [opened[1][k][0] for k in range(qd)])
-    return Proof(Commitments(trace_commit, quotient_commit), ov, opening_proof, log_degree)
+    return Proof(Commitments(trace_commit, quotient_commit), ov, opening_proof, log_degree, blob[split:])

@@ -304,6 +304,11 @@ def check_stark_prove_verify(ts, ctx, orc, air, trace, public_values, log_blowup
     proof = st.prove(pcs, air, ts.BfChallenger(), trace, public_values)
     assert proof.commitments.trace == root and proof.degree_bits == log_n
     assert OS.verify(log_blowup, num_queries, pow_bits, air, orc.BfChallenger(), proof, public_values, log_qd)
+    # serialized proof bytes (uni-stark/src/proof.rs:19-37, postcard): the product's bytes -- its opening_proof part is
+    # what ts_pcs_open emitted, verbatim -- equal the oracle's independent encoding of the decoded proof objects
+    from oracle import serialize as S
+
+    assert proof.to_bytes() == S.encode_stark_proof(proof)
     if not tamper:
         return proof
     # (3) rejection

@@ -434,6 +434,49 @@ def test_pcs_open_verify(ts, ctx, orc):
     pc.check_pcs_open_verify(ts, ctx, orc, [[(8, 12, 2)], [(8, 4, 1)]], 2, num_queries=16, pow_bits=8, seed=110)
 
 
+def test_config4_open_at_scale(ts, ctx, orc):
+    """BASELINE config 4 through Pcs::open in ONE C-ABI call (ts_pcs_open): a 2^21 x 200 trace opened at zeta and
+    zeta*g plus four 2^21 x 4 quotient chunks (their own cosets, uni-stark/src/prover.rs:78-83) opened at zeta, 28 queries,
+    8 proof-of-work bits.  The bytes decode to a proof the restated reference verifier (two_adic_pcs.rs:421-530,
+    fri/src/verifier.rs) accepts; a flipped opened value is rejected.  A wrong opened value anywhere would also make the
+    reduced opening high-degree, i.e. the commit phase's final layer non-constant (prover.rs:130-134)."""
+    import importlib
+
+    from oracle import verifier as V
+
+    log_n, w, b, nq, pow_bits = 21, 200, 2, 28, 8
+    n = 1 << log_n
+    mm = ts.Blake3MerkleMmcs(ctx)
+    pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(b, nq, pow_bits, mm))
+    ch, och = ts.BfChallenger(), orc.BfChallenger()
+    trace = ts.DeviceMatrix.splitmix(ctx, 4, n, w)
+    root_t, data_t = pcs.commit([(pcs.natural_domain_for_degree(n), trace)])
+    ch.observe(root_t)
+    och.observe_digest(root_t)
+    gen22 = orc.two_adic_generator(log_n + 2)
+    chunks = [ts.DeviceMatrix.splitmix(ctx, 10 + k, n, 4) for k in range(4)]
+    doms = [ts.TwoAdicMultiplicativeCoset(log_n, 31 * pow(gen22, k, P) % P) for k in range(4)]  # split_domains
+    root_q, data_q = pcs.commit(list(zip(doms, chunks)))
+    ch.observe(root_q)
+    och.observe_digest(root_q)
+    zeta = [int(x) for x in ch.sample()]
+    assert zeta == [int(x) for x in och.sample_ef()]
+    g = orc.two_adic_generator(log_n)
+    zeta_next = [c * g % P for c in zeta]
+    rounds = [(data_t, [[zeta, zeta_next]]), (data_q, [[zeta]] * 4)]
+    och_v = och.clone()
+    blob = pcs.open_bytes(rounds, ch)
+    opened, proof = importlib.import_module("tapstark_b200.proofio").decode_opening(blob)
+    assert len(proof.query_proofs) == nq and len(proof.commit_phase_commits) == log_n
+    assert opened[0][0][0].shape == (w, 4) and opened[1][3][0].shape == (4, 4)
+    v_rounds = [(root_t, [(log_n, [(zeta, opened[0][0][0].tolist()), (zeta_next, opened[0][0][1].tolist())])]),
+                (root_q, [(log_n, [(zeta, opened[1][k][0].tolist())]) for k in range(4)])]
+    assert V.pcs_verify(b, nq, pow_bits, v_rounds, proof, och_v.clone())
+    v_rounds[0][1][0][1][0][1][7][2] = (v_rounds[0][1][0][1][0][1][7][2] + 1) % P
+    with pytest.raises(V.VerifyError):
+        V.pcs_verify(b, nq, pow_bits, v_rounds, proof, och_v.clone())
+
+
 def test_stark_fibonacci_config1(ts, ctx, orc):
     """BASELINE config 1: Fibonacci AIR, 2^10 x 2 trace, log_blowup 2 -- uni_stark::prove on the device path
     (trace commit -> quotient values kernel -> quotient commit -> open at zeta, zeta*g -> FRI), verified by the
