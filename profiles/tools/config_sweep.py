@@ -55,6 +55,43 @@ def fri_sweep():
         lde.free()
 
 
+def fold_rates():
+    """fold_ext_kernel alone (fri/src/two_adic_pcs.rs:116-147): streaming read-2 / write-1, 48 bytes per output extension
+    element, against the measured HBM peak; layers of 2^22 .. 2^26 elements (C5's largest is 1 GiB in, 512 MiB out)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from __graft_entry__ import load_pkg
+
+    ts = load_pkg()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = ts.Context(0, stream.cuda_stream)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    beta = ts.to_monty(np.array([3, 1, 4, 1], dtype=np.uint32))
+    for log_len in (22, 24, 26):
+        n = 1 << log_len
+        src = torch.randint(0, ts.P, (n, 4), dtype=torch.int32, device="cuda")
+        dst = torch.empty((n // 2, 4), dtype=torch.int32, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for rep in range(6):
+            e0.record(stream)
+            ctx.check(ctx._L.ts_fri_fold_ext(ctx._h, C.c_void_p(src.data_ptr()), n // 2, beta.ctypes.data_as(C.c_void_p), C.c_void_p(dst.data_ptr())), "fold")
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if rep >= 2 and (best is None or ms < best):
+                best = ms
+        gbs = (n // 2) * 48 / (best * 1e-3) / 1e9
+        print(json.dumps({"case": "fold_ext_kernel alone", "log_len_in": log_len, "ms": round(best, 4), "achieved_GBs": round(gbs, 1),
+                          "hbm_peak_GBs": peak, "frac": round(gbs / peak, 3)}))
+        del src, dst
+    ctx.close()
+
+
 def open_c4():
     """Pcs::open at the C4 shape through ts_pcs_open: per-kernel-class device times (the context's CUDA-event statistics)
     and the HBM rate of the dominant passes (alpha-reduction reads the LDE once per matrix, the barycentric sums read the
@@ -102,7 +139,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "open":
         open_c4()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fold":
+        fold_rates()
+        sys.exit(0)
     bench("C2: 2^20 x 64, log_blowup 2", 20, 64, 2)
     bench("C4 trace shape: 2^21 x 200, log_blowup 2", 21, 200, 2)
     fri_sweep()
+    fold_rates()
     open_c4()

@@ -52,3 +52,4 @@ def run(name, air, log_n, log_blowup, n_pub):
 run("fibonacci 2^22 x 2, blowup 4", airs.FibonacciAir(), 22, 2, 3)
 run("mul_air degree 3, 20 triples (width 60), 2^20, blowup 4", airs.MulAir(3, 20), 20, 2, 0)
 run("mul_air degree 5, 20 triples (width 60), 2^19, blowup 8", airs.MulAir(5, 20), 19, 3, 0)
+run("C4 scale: mul_air degree 3, 66 triples (width 198), 2^21, blowup 4", airs.MulAir(3, 66), 21, 2, 0)

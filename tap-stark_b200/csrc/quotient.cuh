@@ -45,10 +45,13 @@ struct Params {
     uint32_t *out[MAX_CHUNKS]; // chunk k: (m >> log_chunks) x 4 words, natural order on its own coset
 };
 
+constexpr int QV_NT = 128;  // threads per CTA; the register file of the constraint program lives in shared memory as
+                            // reg[index][thread] (one bank per thread: conflict free), not in per-thread local memory
+
 TS_D uint32_t operand(const Params &p, uint32_t code, const uint32_t *reg, size_t local_row, size_t next_row, const uint32_t *sel) {
     const uint32_t kind = code >> 28, idx = code & 0x0fffffffu;
     switch (kind) {
-        case K_REG: return reg[idx];
+        case K_REG: return reg[idx * QV_NT];
         case K_LOCAL: return p.lde[local_row * p.width + idx];
         case K_NEXT: return p.lde[next_row * p.width + idx];
         case K_PUBLIC: return p.publics[idx];
@@ -58,7 +61,8 @@ TS_D uint32_t operand(const Params &p, uint32_t code, const uint32_t *reg, size_
 }
 
 // one thread per committed row t (natural quotient-domain index i = brev(t))
-__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
+__global__ void __launch_bounds__(QV_NT) quotient_values_kernel(Params p) {
+    TS_DYN_SMEM(uint32_t, regfile);  // MAX_REGS x QV_NT words
     const size_t m = (size_t)1 << p.log_m;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
     sel[0] = bb::mmul(zh, bb::mmul(inv_both, d_last));
     sel[1] = bb::mmul(zh, bb::mmul(inv_both, d_first));
     sel[2] = d_last;
-    uint32_t reg[MAX_REGS];
+    uint32_t *reg = regfile + threadIdx.x;
     ef::E4 acc{{0, 0, 0, 0}};
     const ef::E4Const ka = ef::prepare(p.alpha);
     for (uint32_t pc = 0; pc < p.n_instr; pc++) {
@@ -88,11 +92,11 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
             continue;
         }
         if (op == OP_NEG) {
-            reg[dst] = bb::neg(a);
+            reg[dst * QV_NT] = bb::neg(a);
             continue;
         }
         const uint32_t b = operand(p, p.program[4 * pc + 3], reg, t, next_row, sel);
-        reg[dst] = op == OP_ADD ? bb::add(a, b) : op == OP_SUB ? bb::sub(a, b) : bb::mmul(a, b);
+        reg[dst * QV_NT] = op == OP_ADD ? bb::add(a, b) : op == OP_SUB ? bb::sub(a, b) : bb::mmul(a, b);
     }
     const uint32_t izh = p.zh_inv[i & zmask];
     const uint32_t qd_mask = (1u << p.log_chunks) - 1;

@@ -2378,7 +2378,7 @@ int ts_quotient_values(ts_ctx *c, const ts_matrix *trace_lde, unsigned log_n, un
     if (rc == TS_OK) {
         KScope ks(c, TS_K_MISC);
         auto kfn = quo::quotient_values_kernel;
-        TS_LAUNCH(kfn, (unsigned)((m + 127) / 128), 128, 0, c->stream, p);
+        TS_LAUNCH(kfn, (unsigned)((m + quo::QV_NT - 1) / quo::QV_NT), quo::QV_NT, (size_t)quo::MAX_REGS * quo::QV_NT * 4, c->stream, p);
         rc = check_launch(c, "quotient_values_kernel");
     }
     pool_release(c, dev);  // stream-ordered

@@ -38,7 +38,7 @@ class ShardedProver:
 
         self.peer_lanes = max(1, min(7, int(os.environ.get("TS_PEER_LANES", "3"))))  # copy queues of the copy-engine re-shard
         if "TS_REPLICATE_BELOW" in os.environ:  # measurement hook: FRI layers of at most this many elements are gathered
-            self.REPLICATE_BELOW = int(os.environ["TS_REPLICATE_BELOW"])
+            self.REPLICATE_BELOW = self.MAILBOX_REPLICATE_BELOW = int(os.environ["TS_REPLICATE_BELOW"])
         if device.type == "cuda":
             # torch tensors, the NCCL collectives and the caching allocator's frees are ordered on torch's current stream; the
             # library's kernels run on the context's stream.  They must be ONE stream ("Multi-GPU"): a
@@ -210,6 +210,7 @@ class ShardedProver:
 
     # ---- the step -------------------------------------------------------------------------------------
     REPLICATE_BELOW = 1 << 20  # FRI layers of at most this many elements are gathered and folded on every rank
+    MAILBOX_REPLICATE_BELOW = 1 << 20  # the same threshold when sub-roots travel through peer mailboxes (measured per N)
 
     def _chunks(self, wl: int) -> int:
         """column chunks per rank: the LDE of chunk c+1 overlaps the all-to-all of chunk c (NCCL runs on its own
@@ -473,6 +474,8 @@ class ShardedProver:
 
     def _fri_commit_phase(self, cur_t, len_g: int, ch):
         """fri/src/prover.rs:93-141 on a row-sharded codeword (cur_t: this rank's [len_g/G, 4] slice)."""
+        import os
+
         ts, ctx, torch, dist, G, r = self.ts, self.ctx, self.torch, self.dist, self.world, self.rank
         L = ctx._L
         commits: List[bytes] = []
@@ -484,7 +487,15 @@ class ShardedProver:
         lg, lc = len_g, local
         while lg > blowup and lg > self.REPLICATE_BELOW and (lc // 2) >= 256 and (lc // 2) * G == lg // 2:
             sharded, lg, lc = sharded + 1, lg // 2, lc // 2
-        mail = self._mailbox_setup() if sharded else None
+        mail = self._mailbox_setup() if (sharded or G > 1) else None
+        if mail is not None and "TS_REPLICATE_BELOW" not in os.environ and self.REPLICATE_BELOW == type(self).REPLICATE_BELOW:
+            # with the mailbox exchange a sharded round costs a few small launches and no host work: keep sharding down to
+            # MAILBOX_REPLICATE_BELOW elements (the fold wants at least 256 local rows)
+            sharded, lg, lc = 0, len_g, local
+            while lg > blowup and lg > self.MAILBOX_REPLICATE_BELOW and (lc // 2) >= 256 and (lc // 2) * G == lg // 2:
+                sharded, lg, lc = sharded + 1, lg // 2, lc // 2
+            if sharded == 0:
+                mail = None
         if mail is not None:
             # every sharded round in ONE library call; the sub-roots travel through peer-mapped mailboxes inside the kernels
             self._epoch = getattr(self, "_epoch", 0) + 1
