@@ -250,6 +250,14 @@ int ts_taptree_commit(ts_ctx *ctx, const ts_matrix *leaf_rows, const uint8_t *se
 int ts_taptree_leaf_indices(ts_ctx *ctx, const ts_taptree *t, uint32_t *out_host);
 int ts_taptree_level(ts_ctx *ctx, const ts_taptree *t, unsigned level, uint8_t *out_host);
 void ts_taptree_free(ts_taptree *t);
+/* The rows the leaves commit to when several matrices of different heights share one tree: PolyTCS::padding_matrix
+ * (basic/src/tcs/mod.rs:341-383) -- matrices tallest first (stable), a matrix of height h repeats each of its rows over
+ * hmax / h consecutive leaves, rows concatenated.  Heights are powers of two.  *out: hmax x (sum of widths), Montgomery. */
+int ts_padded_leaf_rows(ts_ctx *ctx, const ts_matrix *const *mats, size_t n_mats, ts_matrix **out);
+/* CommitedData::query_proof (basic/src/tcs/mod.rs:141-146) without the script bytes: the TaprootMerkleBranch of Merkle leaf
+ * `index` (log2(n_leaves) sibling hashes of 32 bytes, leaf level first; verify_inclusion, complete_taptree.rs:64-73, folds
+ * them with sorted pairs) and its position among the TapTree's leaves (leaf_indices[index]; may be NULL). */
+int ts_taptree_open(ts_ctx *ctx, const ts_taptree *t, size_t index, uint8_t *path_out, uint32_t *position_out);
 
 /* ---------------------------------------------------------------- quotient values (f3)
  * quotient_values of uni_stark::prove (uni-stark/src/prover.rs:122-194) on the device-resident trace LDE:

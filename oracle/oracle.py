@@ -83,6 +83,9 @@ def lib():
         "or_mmcs_verify_batch": (C.c_int, [szp, szp, C.c_size_t, C.c_int, C.c_size_t, u32p, u8p, C.c_size_t, u8p]),
         "or_tree_free": (None, [C.c_void_p]),
         "or_padded_leaf": (C.c_size_t, [C.POINTER(u32p), szp, szp, C.c_size_t, C.c_size_t, u32p]),
+        "or_sha256": (None, [u8p, C.c_size_t, u8p]),
+        "or_tap_leaf_hash": (None, [u8p, C.c_size_t, u8p]),
+        "or_tap_branch_hash": (None, [u8p, u8p, u8p]),
         "or_fold_matrix_bb": (None, [u32p, C.c_uint, C.c_uint32, u32p]),
         "or_fold_matrix_ef": (None, [u32p, C.c_uint, u32p, u32p]),
         "or_fold_row_ef": (None, [C.c_size_t, C.c_uint, u32p, u32p, u32p, u32p]),

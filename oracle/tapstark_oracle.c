@@ -796,3 +796,79 @@ int or_fri_commit_phase(const uint32_t *const *inputs, const size_t *lens, size_
     free(folded);
     return ok ? rounds : -1;
 }
+
+/* ---- SHA-256 (FIPS 180-4) + BIP-341 tagged hashes ------------------------------------------------------------------ */
+static const uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void sha_block(uint32_t h[8], const uint8_t b[64]) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)b[4 * i] << 24) | ((uint32_t)b[4 * i + 1] << 16) | ((uint32_t)b[4 * i + 2] << 8) | b[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        const uint32_t s0 = sha_rotr(w[i - 15], 7) ^ sha_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        const uint32_t s1 = sha_rotr(w[i - 2], 17) ^ sha_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t v[8];
+    memcpy(v, h, 32);
+    for (int i = 0; i < 64; i++) {
+        const uint32_t S1 = sha_rotr(v[4], 6) ^ sha_rotr(v[4], 11) ^ sha_rotr(v[4], 25), ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+        const uint32_t t1 = v[7] + S1 + ch + SHA_K[i] + w[i];
+        const uint32_t S0 = sha_rotr(v[0], 2) ^ sha_rotr(v[0], 13) ^ sha_rotr(v[0], 22), mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+        v[7] = v[6], v[6] = v[5], v[5] = v[4], v[4] = v[3] + t1, v[3] = v[2], v[2] = v[1], v[1] = v[0], v[0] = t1 + S0 + mj;
+    }
+    for (int i = 0; i < 8; i++) h[i] += v[i];
+}
+/* SHA-256 of prefix (may be empty) followed by data */
+static void sha256_two(const uint8_t *pre, size_t pre_len, const uint8_t *data, size_t len, uint8_t out[32]) {
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint8_t buf[64];
+    size_t fill = 0;
+    const uint64_t total = (uint64_t)pre_len + len;
+    for (int part = 0; part < 2; part++) {
+        const uint8_t *p = part ? data : pre;
+        const size_t n = part ? len : pre_len;
+        for (size_t i = 0; i < n; i++) {
+            buf[fill++] = p[i];
+            if (fill == 64) sha_block(h, buf), fill = 0;
+        }
+    }
+    buf[fill++] = 0x80;
+    if (fill > 56) {
+        memset(buf + fill, 0, 64 - fill);
+        sha_block(h, buf);
+        fill = 0;
+    }
+    memset(buf + fill, 0, 56 - fill);
+    for (int i = 0; i < 8; i++) buf[56 + i] = (uint8_t)((total * 8) >> (56 - 8 * i));
+    sha_block(h, buf);
+    for (int i = 0; i < 8; i++) out[4 * i] = (uint8_t)(h[i] >> 24), out[4 * i + 1] = (uint8_t)(h[i] >> 16), out[4 * i + 2] = (uint8_t)(h[i] >> 8), out[4 * i + 3] = (uint8_t)h[i];
+}
+void or_sha256(const uint8_t *data, size_t len, uint8_t out[32]) { sha256_two(NULL, 0, data, len, out); }
+static void tagged_hash(const char *tag, const uint8_t *pre, size_t pre_len, const uint8_t *data, size_t len, uint8_t out[32]) {
+    uint8_t t[32];
+    or_sha256((const uint8_t *)tag, strlen(tag), t);
+    uint8_t *m = (uint8_t *)malloc(64 + pre_len + len + 1);
+    memcpy(m, t, 32), memcpy(m + 32, t, 32);
+    if (pre_len) memcpy(m + 64, pre, pre_len);
+    if (len) memcpy(m + 64 + pre_len, data, len);
+    or_sha256(m, 64 + pre_len + len, out);
+    free(m);
+}
+void or_tap_leaf_hash(const uint8_t *script, size_t len, uint8_t out[32]) {
+    uint8_t pre[6] = {0xc0};
+    size_t n = 1;
+    if (len < 0xfd) pre[n++] = (uint8_t)len;
+    else if (len <= 0xffff) pre[n++] = 0xfd, pre[n++] = (uint8_t)len, pre[n++] = (uint8_t)(len >> 8);
+    else pre[n++] = 0xfe, pre[n++] = (uint8_t)len, pre[n++] = (uint8_t)(len >> 8), pre[n++] = (uint8_t)(len >> 16), pre[n++] = (uint8_t)(len >> 24);
+    tagged_hash("TapLeaf", pre, n, script, len, out);
+}
+void or_tap_branch_hash(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+    const int a_first = memcmp(a, b, 32) <= 0;
+    tagged_hash("TapBranch", a_first ? a : b, 32, a_first ? b : a, 32, out);
+}

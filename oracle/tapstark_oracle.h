@@ -85,6 +85,13 @@ void or_tree_free(or_tree *t);
 size_t or_padded_leaf(const uint32_t *const *mats, const size_t *heights, const size_t *widths,
                       size_t k, size_t leaf, uint32_t *out);
 
+/* ---- SHA-256 (FIPS 180-4) and the BIP-341 tagged hashes of the TapTree commitment (basic/src/tcs/builder.rs:26,64 through
+ * rust-bitcoin [MEM]): TapLeaf = H_tag("TapLeaf", 0xc0 || compact_size(len) || script), TapBranch = H_tag("TapBranch", min || max).
+ * Pinned to hashlib in tests/test_taptree.py. */
+void or_sha256(const uint8_t *data, size_t len, uint8_t out[32]);
+void or_tap_leaf_hash(const uint8_t *script, size_t len, uint8_t out[32]);
+void or_tap_branch_hash(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+
 /* ---- FRI fold (fri/src/two_adic_pcs.rs:116-147 == fri/src/fold_even_odd.rs:20-52) ---------- */
 void or_fold_matrix_bb(const uint32_t *in, unsigned log_h, uint32_t beta, uint32_t *out);
 void or_fold_matrix_ef(const uint32_t *in, unsigned log_h, const uint32_t beta[4], uint32_t *out);

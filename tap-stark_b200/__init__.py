@@ -136,6 +136,8 @@ _SIGNATURES = {
     "ts_taptree_leaf_indices": (C.c_int, [_vp, _vp, _vp]),
     "ts_taptree_level": (C.c_int, [_vp, _vp, C.c_uint, _vp]),
     "ts_taptree_free": (None, [_vp]),
+    "ts_padded_leaf_rows": (C.c_int, [_vp, _vpp, C.c_size_t, _vpp]),
+    "ts_taptree_open": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp]),
     "ts_copy_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_size_t, C.c_int]),
     "ts_copy2d_async": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]),
     "ts_copy_join": (C.c_int, [_vp, C.c_int]),
@@ -560,6 +562,14 @@ class TapTreeCommit:
         out = np.empty((self.n_leaves >> level, 32), dtype=np.uint8)
         self.ctx.check(self.ctx._L.ts_taptree_level(self.ctx._h, self._h, level, _ptr(out)), "taptree_level")
         return out
+
+    def open(self, index: int) -> Tuple[List[bytes], int]:
+        """(TaprootMerkleBranch of Merkle leaf `index`, leaf level first; its position among the TapTree's leaves)."""
+        depth = self.n_leaves.bit_length() - 1
+        path = np.zeros((max(depth, 1), 32), dtype=np.uint8)
+        pos = C.c_uint32(0)
+        self.ctx.check(self.ctx._L.ts_taptree_open(self.ctx._h, self._h, index, _ptr(path), C.byref(pos)), "taptree_open")
+        return [bytes(path[l]) for l in range(depth)], int(pos.value)
 
     def free(self):
         if self._h:

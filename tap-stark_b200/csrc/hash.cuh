@@ -418,6 +418,19 @@ __global__ void __launch_bounds__(128) tree_reduce3_kernel(const uint32_t *__res
     o[1] = make_uint4(r8[4], r8[5], r8[6], r8[7]);
 }
 
+// padding_matrix (basic/src/tcs/mod.rs:341-383) materialised: out[leaf] = concat_s row_s[leaf >> shift_s], the row of field words
+// a TapTree leaf commits to (matrices tallest first; a shorter matrix repeats each row over 2^shift consecutive leaves).
+__global__ void __launch_bounds__(256) padded_rows_kernel(Segments sg, size_t n_leaves, uint32_t *__restrict__ out) {
+    const size_t total = n_leaves * sg.total_words;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t leaf = i / sg.total_words;
+        uint32_t off = (uint32_t)(i % sg.total_words);
+        int s = 0;
+        while (off >= sg.width[s]) { off -= sg.width[s]; s++; }
+        out[i] = sg.ptr[s][(leaf >> sg.shift[s]) * sg.width[s] + off];
+    }
+}
+
 // P3 injection layer: out[i] = H( H(prev[2i] || prev[2i+1]) || rows_digest[i] )
 __global__ void compress_inject_kernel(const uint32_t *children, const uint32_t *rows_digest, size_t n_par,
                                        uint32_t *out) {

@@ -69,49 +69,80 @@ __global__ void __launch_bounds__(256) inv_denoms_kernel(uint4 *out, int log_h, 
     }
 }
 
-// Barycentric column sums over the low coset: partial[blk][c] = sum_{r in block rows} e[r][c] * k_r,
-// k_r = x_r * inv_denom[r] (the sign and the (z/g)^n - 1)/n factor are applied by the caller).
-// One thread per column (coalesced row reads), RB rows per CTA, k_r staged in shared memory.
+// Barycentric column sums over the low coset: partial[cta][c] = sum_{r in the CTA's row blocks} e[r][c] * k_r,
+// k_r = x_r * inv_denom[r] (the sign and the ((z/g)^n - 1)/n factor are applied by the caller).
+// The 256 threads of a CTA are (256 >> tpr_log) row lanes x (1 << tpr_log) columns -- one lane for a 200-column trace
+// (coalesced 800-byte row reads), 64 lanes for a 4-column quotient chunk -- and a CTA walks the row blocks grid-stride with
+// its sums in registers, so the number of partials is the grid size (a few per SM), not n / 128: the second kernel used to
+// add 16384 partials per column in ONE serial loop per thread, which was most of the time of Pcs::open at the C4 shape.
 constexpr int BARY_RB = 128;
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__restrict__ m, size_t n, uint32_t width, int log_h,
                                                           uint32_t g_monty, RootPows rp, const uint4 *__restrict__ inv_denoms,
-                                                          uint4 *__restrict__ partial) {
-    TS_DYN_SMEM(uint32_t, ks);  // BARY_RB x 4
-    const size_t r0 = (size_t)blockIdx.x * BARY_RB;
-    for (int i = threadIdx.x; i < BARY_RB; i += blockDim.x) {
-        uint4 k = make_uint4(0, 0, 0, 0);
-        if (r0 + i < n) {
-            const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)(r0 + i), log_h)));
-            const uint4 d = inv_denoms[r0 + i];
-            k = make_uint4(bb::mmul(x, d.x), bb::mmul(x, d.y), bb::mmul(x, d.z), bb::mmul(x, d.w));
-        }
-        ks[4 * i + 0] = k.x; ks[4 * i + 1] = k.y; ks[4 * i + 2] = k.z; ks[4 * i + 3] = k.w;
-    }
-    __syncthreads();
-    for (uint32_t c = threadIdx.x; c < width; c += blockDim.x) {
+                                                          uint4 *__restrict__ partial, int tpr_log) {
+    TS_DYN_SMEM(uint32_t, ks);  // BARY_RB x 4 weights, then 256 x 4 words for the lane reduction
+    uint32_t *red = ks + BARY_RB * 4;
+    const uint32_t tpr = 1u << tpr_log, lanes = 256u >> tpr_log;
+    const uint32_t lane = threadIdx.x >> tpr_log, cl = threadIdx.x & (tpr - 1);
+    const size_t n_blocks = (n + BARY_RB - 1) / BARY_RB;
+    for (uint32_t c0 = 0; c0 < width; c0 += tpr) {
+        const uint32_t c = c0 + cl;
         uint32_t acc[4] = {0, 0, 0, 0};
-        for (int i = 0; i < BARY_RB; i += 2) {
-            const uint32_t v0 = r0 + i < n ? m[(r0 + i) * width + c] : 0u;
-            const uint32_t v1 = r0 + i + 1 < n ? m[(r0 + i + 1) * width + c] : 0u;
-            TS_UNROLL
-            for (int k = 0; k < 4; k++)
-                acc[k] = bb::add(acc[k], bb::redc((uint64_t)v0 * ks[4 * i + k] + (uint64_t)v1 * ks[4 * i + 4 + k]));
+        for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+            const size_t r0 = blk * BARY_RB;
+            __syncthreads();
+            for (int i = threadIdx.x; i < BARY_RB; i += blockDim.x) {
+                uint4 k = make_uint4(0, 0, 0, 0);
+                if (r0 + i < n) {
+                    const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)(r0 + i), log_h)));
+                    const uint4 d = inv_denoms[r0 + i];
+                    k = make_uint4(bb::mmul(x, d.x), bb::mmul(x, d.y), bb::mmul(x, d.z), bb::mmul(x, d.w));
+                }
+                ks[4 * i + 0] = k.x; ks[4 * i + 1] = k.y; ks[4 * i + 2] = k.z; ks[4 * i + 3] = k.w;
+            }
+            __syncthreads();
+            if (c < width)
+                for (uint32_t i = 2 * lane; i < (uint32_t)BARY_RB; i += 2 * lanes) {
+                    const uint32_t v0 = r0 + i < n ? m[(r0 + i) * width + c] : 0u;
+                    const uint32_t v1 = r0 + i + 1 < n ? m[(r0 + i + 1) * width + c] : 0u;
+                    TS_UNROLL
+                    for (int k = 0; k < 4; k++)
+                        acc[k] = bb::add(acc[k], bb::redc((uint64_t)v0 * ks[4 * i + k] + (uint64_t)v1 * ks[4 * i + 4 + k]));
+                }
         }
-        partial[(size_t)blockIdx.x * width + c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        TS_UNROLL
+        for (int k = 0; k < 4; k++) red[4 * threadIdx.x + k] = acc[k];
+        __syncthreads();
+        if (lane == 0 && c < width) {
+            for (uint32_t l = 1; l < lanes; l++) {
+                TS_UNROLL
+                for (int k = 0; k < 4; k++) acc[k] = bb::add(acc[k], red[4 * ((l << tpr_log) + cl) + k]);
+            }
+            partial[(size_t)blockIdx.x * width + c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        }
     }
 }
-// ys[c] = sum_blk partial[blk][c]
-__global__ void __launch_bounds__(256) bary_final_kernel(const uint4 *__restrict__ partial, size_t n_blocks, uint32_t width,
+// ys[c] = sum_cta partial[cta][c]; 32 columns x 8 partial lanes per CTA
+__global__ void __launch_bounds__(256) bary_final_kernel(const uint4 *__restrict__ partial, size_t n_partials, uint32_t width,
                                                         uint4 *__restrict__ ys) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= width) return;
+    TS_DYN_SMEM(uint32_t, red);  // 256 x 4
+    const uint32_t c = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
     uint32_t acc[4] = {0, 0, 0, 0};
-    for (size_t b = 0; b < n_blocks; b++) {
-        const uint4 p = partial[b * width + c];
-        acc[0] = bb::add(acc[0], p.x); acc[1] = bb::add(acc[1], p.y);
-        acc[2] = bb::add(acc[2], p.z); acc[3] = bb::add(acc[3], p.w);
+    if (c < width)
+        for (size_t b = ty; b < n_partials; b += 8) {
+            const uint4 p = partial[b * width + c];
+            acc[0] = bb::add(acc[0], p.x); acc[1] = bb::add(acc[1], p.y);
+            acc[2] = bb::add(acc[2], p.z); acc[3] = bb::add(acc[3], p.w);
+        }
+    TS_UNROLL
+    for (int k = 0; k < 4; k++) red[4 * threadIdx.x + k] = acc[k];
+    __syncthreads();
+    if (ty == 0 && c < width) {
+        for (uint32_t l = 1; l < 8; l++) {
+            TS_UNROLL
+            for (int k = 0; k < 4; k++) acc[k] = bb::add(acc[k], red[4 * (32 * l + threadIdx.x) + k]);
+        }
+        ys[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
     }
-    ys[c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // ro[X] += apo * (dot[X] - rys) * inv_denoms[X]

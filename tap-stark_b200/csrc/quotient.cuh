@@ -45,13 +45,10 @@ struct Params {
     uint32_t *out[MAX_CHUNKS]; // chunk k: (m >> log_chunks) x 4 words, natural order on its own coset
 };
 
-constexpr int QV_NT = 128;  // threads per CTA; the register file of the constraint program lives in shared memory as
-                            // reg[index][thread] (one bank per thread: conflict free), not in per-thread local memory
-
 TS_D uint32_t operand(const Params &p, uint32_t code, const uint32_t *reg, size_t local_row, size_t next_row, const uint32_t *sel) {
     const uint32_t kind = code >> 28, idx = code & 0x0fffffffu;
     switch (kind) {
-        case K_REG: return reg[idx * QV_NT];
+        case K_REG: return reg[idx];
         case K_LOCAL: return p.lde[local_row * p.width + idx];
         case K_NEXT: return p.lde[next_row * p.width + idx];
         case K_PUBLIC: return p.publics[idx];
@@ -60,49 +57,52 @@ TS_D uint32_t operand(const Params &p, uint32_t code, const uint32_t *reg, size_
     }
 }
 
-// one thread per committed row t (natural quotient-domain index i = brev(t))
-__global__ void __launch_bounds__(QV_NT) quotient_values_kernel(Params p) {
-    TS_DYN_SMEM(uint32_t, regfile);  // MAX_REGS x QV_NT words
+// One thread per committed row t (natural quotient-domain index i = brev(t)), grid-stride.  The register file of the
+// constraint program is per-thread local memory ON PURPOSE: a thread reads its two trace rows column by column, 32 threads of
+// a warp touch 32 different rows per load, and only the L1 turns those 4-byte reads into one 128-byte line fetch per 32
+// columns.  Moving the register file into shared memory (tried in round 2: reg[index][thread], conflict free) shrinks the
+// L1 by the carve-out and made the kernel 3x SLOWER (width 60: 1.64 ms against 0.53 ms; profiles/r02/README.md).
+__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
     const size_t m = (size_t)1 << p.log_m;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    const uint32_t i = opn::brev_bits((uint32_t)t, p.log_m);
     const uint32_t next_step = 1u << (p.log_m - p.log_n);                       // prover.rs:141-142
-    const uint32_t i_next = (i + next_step) & (uint32_t)(m - 1);
-    const size_t next_row = opn::brev_bits(i_next, p.log_m);
-    // selectors at x = g w_m^i
-    const uint32_t x = bb::mmul(p.g_monty, opn::pow_from_table(p.rp, i));
     const uint32_t zmask = next_step - 1;
-    const uint32_t zh = p.zh[i & zmask];
-    const uint32_t d_first = bb::sub(x, bb::MONTY_ONE), d_last = bb::sub(x, p.wn_inv);
-    const uint32_t inv_both = opn::bb_inv(bb::mmul(d_first, d_last));           // one inversion for both denominators
-    uint32_t sel[3];
-    sel[0] = bb::mmul(zh, bb::mmul(inv_both, d_last));
-    sel[1] = bb::mmul(zh, bb::mmul(inv_both, d_first));
-    sel[2] = d_last;
-    uint32_t *reg = regfile + threadIdx.x;
-    ef::E4 acc{{0, 0, 0, 0}};
-    const ef::E4Const ka = ef::prepare(p.alpha);
-    for (uint32_t pc = 0; pc < p.n_instr; pc++) {
-        const uint32_t op = p.program[4 * pc], dst = p.program[4 * pc + 1];
-        const uint32_t a = operand(p, p.program[4 * pc + 2], reg, t, next_row, sel);
-        if (op == OP_ASSERT_ZERO) {
-            acc = ef::mul(acc, ka);
-            acc.c[0] = bb::add(acc.c[0], a);
-            continue;
-        }
-        if (op == OP_NEG) {
-            reg[dst * QV_NT] = bb::neg(a);
-            continue;
-        }
-        const uint32_t b = operand(p, p.program[4 * pc + 3], reg, t, next_row, sel);
-        reg[dst * QV_NT] = op == OP_ADD ? bb::add(a, b) : op == OP_SUB ? bb::sub(a, b) : bb::mmul(a, b);
-    }
-    const uint32_t izh = p.zh_inv[i & zmask];
     const uint32_t qd_mask = (1u << p.log_chunks) - 1;
-    uint32_t *o = p.out[i & qd_mask] + (size_t)(i >> p.log_chunks) * 4;
-    *reinterpret_cast<uint4 *>(o) = make_uint4(bb::mmul(acc.c[0], izh), bb::mmul(acc.c[1], izh), bb::mmul(acc.c[2], izh),
-                                               bb::mmul(acc.c[3], izh));
+    const ef::E4Const ka = ef::prepare(p.alpha);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = opn::brev_bits((uint32_t)t, p.log_m);
+        const uint32_t i_next = (i + next_step) & (uint32_t)(m - 1);
+        const size_t next_row = opn::brev_bits(i_next, p.log_m);
+        // selectors at x = g w_m^i
+        const uint32_t x = bb::mmul(p.g_monty, opn::pow_from_table(p.rp, i));
+        const uint32_t zh = p.zh[i & zmask];
+        const uint32_t d_first = bb::sub(x, bb::MONTY_ONE), d_last = bb::sub(x, p.wn_inv);
+        const uint32_t inv_both = opn::bb_inv(bb::mmul(d_first, d_last));       // one inversion for both denominators
+        uint32_t sel[3];
+        sel[0] = bb::mmul(zh, bb::mmul(inv_both, d_last));
+        sel[1] = bb::mmul(zh, bb::mmul(inv_both, d_first));
+        sel[2] = d_last;
+        uint32_t reg[MAX_REGS];
+        ef::E4 acc{{0, 0, 0, 0}};
+        for (uint32_t pc = 0; pc < p.n_instr; pc++) {
+            const uint32_t op = p.program[4 * pc], dst = p.program[4 * pc + 1];
+            const uint32_t a = operand(p, p.program[4 * pc + 2], reg, t, next_row, sel);
+            if (op == OP_ASSERT_ZERO) {
+                acc = ef::mul(acc, ka);
+                acc.c[0] = bb::add(acc.c[0], a);
+                continue;
+            }
+            if (op == OP_NEG) {
+                reg[dst] = bb::neg(a);
+                continue;
+            }
+            const uint32_t b = operand(p, p.program[4 * pc + 3], reg, t, next_row, sel);
+            reg[dst] = op == OP_ADD ? bb::add(a, b) : op == OP_SUB ? bb::sub(a, b) : bb::mmul(a, b);
+        }
+        const uint32_t izh = p.zh_inv[i & zmask];
+        uint32_t *o = p.out[i & qd_mask] + (size_t)(i >> p.log_chunks) * 4;
+        *reinterpret_cast<uint4 *>(o) = make_uint4(bb::mmul(acc.c[0], izh), bb::mmul(acc.c[1], izh), bb::mmul(acc.c[2], izh),
+                                                   bb::mmul(acc.c[3], izh));
+    }
 }
 
 }  // namespace quo

@@ -13,6 +13,8 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <tuple>
 #include <functional>
 #include <vector>
@@ -79,6 +81,14 @@ struct ts_ctx {
     bool ev_free_used[2] = {false, false};
     uint32_t *stage[2] = {nullptr, nullptr};
     size_t stage_words = 0;
+    // pageable host sources (stage_pageable_window): worker threads gather row windows into page-locked bounce slots
+    // and queue 1-D copies on their own streams; two slots per worker, reused across calls
+    static constexpr int BOUNCE_WORKERS = 16;
+    static constexpr size_t BOUNCE_SLOT_BYTES = (size_t)4 << 20;
+    uint8_t *bounce = nullptr;
+    cudaStream_t bounce_stream[BOUNCE_WORKERS] = {};
+    cudaEvent_t bounce_ev[BOUNCE_WORKERS][2] = {}, bounce_done[BOUNCE_WORKERS] = {};
+    bool bounce_ev_used[BOUNCE_WORKERS][2] = {};
     std::multimap<size_t, void *> pool_free;
     std::map<void *, size_t> pool_sizes;
     // stats
@@ -900,6 +910,77 @@ bool incremental_hash_eligible(size_t w) {
            getenv("TS_NO_INC_HASH") == nullptr;
 }
 
+#ifndef TS_EMULATE
+// true when `host` is ordinary pageable memory (neither cudaHostAlloc'ed nor cudaHostRegister'ed)
+bool host_is_pageable(const void *host) {
+    if (getenv("TS_NO_BOUNCE")) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+int bounce_workers() {
+    int t = (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char *e = getenv("TS_BOUNCE_THREADS")) t = atoi(e);
+    return std::max(1, std::min(t, (int)ts_ctx::BOUNCE_WORKERS));
+}
+// Window [col0, col0 + cols) of all n rows of a PAGEABLE row-major n x w host matrix -> dense n x cols device buffer.
+// A strided 2-D copy out of pageable memory is staged row by row by the driver (measured 5.9 GB/s), and page-locking the
+// caller's buffer for the call costs more than the copy (cudaHostRegister of 4 GiB: ~1 s).  Instead worker threads gather
+// blocks of rows into page-locked bounce slots (the strided part, done by the CPU cores in parallel) and queue a dense 1-D
+// copy per block on their own stream; the DMA of one block overlaps the gather of the next.  `after` (optional) is an event
+// the copies must wait for (the destination's previous reader); on return `c->stream` is ordered after all copies.
+int stage_pageable_window(ts_ctx *c, const uint32_t *host, size_t n, size_t w, size_t col0, size_t cols, uint32_t *dev,
+                          cudaEvent_t after) {
+    const int T = bounce_workers();
+    if (!c->bounce) {
+        TS_CUDA(c, cudaHostAlloc((void **)&c->bounce, ts_ctx::BOUNCE_WORKERS * 2 * ts_ctx::BOUNCE_SLOT_BYTES, cudaHostAllocDefault));
+        for (int t = 0; t < ts_ctx::BOUNCE_WORKERS; t++) {
+            TS_CUDA(c, cudaStreamCreateWithFlags(&c->bounce_stream[t], cudaStreamNonBlocking));
+            TS_CUDA(c, cudaEventCreateWithFlags(&c->bounce_ev[t][0], cudaEventDisableTiming));
+            TS_CUDA(c, cudaEventCreateWithFlags(&c->bounce_ev[t][1], cudaEventDisableTiming));
+            TS_CUDA(c, cudaEventCreateWithFlags(&c->bounce_done[t], cudaEventDisableTiming));
+        }
+    }
+    const size_t row_bytes = cols * 4;
+    const size_t rows_per_block = std::max<size_t>(1, ts_ctx::BOUNCE_SLOT_BYTES / row_bytes);
+    const size_t nblocks = (n + rows_per_block - 1) / rows_per_block;
+    std::atomic<int> failed{(int)cudaSuccess};
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(c->device);
+        if (e == cudaSuccess && after) e = cudaStreamWaitEvent(c->bounce_stream[t], after, 0);
+        size_t k = 0;
+        for (size_t blk = (size_t)t; blk < nblocks && e == cudaSuccess; blk += (size_t)T, k++) {
+            const int slot = (int)(k & 1);
+            uint8_t *buf = c->bounce + ((size_t)t * 2 + slot) * ts_ctx::BOUNCE_SLOT_BYTES;
+            if (c->bounce_ev_used[t][slot]) e = cudaEventSynchronize(c->bounce_ev[t][slot]);  // the slot's previous copy
+            if (e != cudaSuccess) break;
+            const size_t r0 = blk * rows_per_block, r1 = std::min(n, r0 + rows_per_block);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(host + r0 * w + col0);
+            for (size_t r = r0; r < r1; r++, src += w * 4) memcpy(buf + (r - r0) * row_bytes, src, row_bytes);
+            e = cudaMemcpyAsync(dev + r0 * cols, buf, (r1 - r0) * row_bytes, cudaMemcpyHostToDevice, c->bounce_stream[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(c->bounce_ev[t][slot], c->bounce_stream[t]);
+            c->bounce_ev_used[t][slot] = true;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(c->bounce_done[t], c->bounce_stream[t]);
+        if (e != cudaSuccess) failed.store((int)e);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    if (failed.load() != (int)cudaSuccess) {
+        for (int t = 0; t < T; t++) cudaStreamSynchronize(c->bounce_stream[t]);  // nothing of ours left in flight
+        c->err = std::string("pageable staging: ") + cudaGetErrorString((cudaError_t)failed.load());
+        return TS_ERR_CUDA;
+    }
+    for (int t = 0; t < T; t++) TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->bounce_done[t], 0));
+    return TS_OK;
+}
+#endif
+
 // leaf_digests != nullptr: also absorb every finished chunk into the row hashes (incremental_hash_eligible(w)), so
 // that only the last chunk's blocks remain to be hashed when the copy ends.
 int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w, unsigned b, uint32_t shift_monty,
@@ -935,17 +1016,25 @@ int lde_from_host_pipelined(ts_ctx *c, const uint32_t *host, size_t n, size_t w,
         }
     }
 #endif
+#ifndef TS_EMULATE
+    const bool pageable = host_is_pageable(host);
+#endif
     for (size_t ch = 0; ch < nchunks; ch++) {
         const int s = (int)(ch & 1);
         const size_t col0 = sched[ch].first, cols = sched[ch].second;
 #ifndef TS_EMULATE
-        if (c->ev_free_used[s]) TS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
-#endif
+        if (pageable) {
+            TS_TRY(stage_pageable_window(c, host, n, w, col0, cols, c->stage[s], c->ev_free_used[s] ? c->ev_free[s] : nullptr));
+        } else {
+            if (c->ev_free_used[s]) TS_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
+            TS_CUDA(c, cudaMemcpy2DAsync(c->stage[s], cols * 4, host + col0, w * 4, cols * 4, n, cudaMemcpyHostToDevice,
+                                         c->copy_stream));
+            TS_CUDA(c, cudaEventRecord(c->ev_copy[s], c->copy_stream));
+            TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[s], 0));
+        }
+#else
         TS_CUDA(c, cudaMemcpy2DAsync(c->stage[s], cols * 4, host + col0, w * 4, cols * 4, n, cudaMemcpyHostToDevice,
                                      c->copy_stream));
-#ifndef TS_EMULATE
-        TS_CUDA(c, cudaEventRecord(c->ev_copy[s], c->copy_stream));
-        TS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[s], 0));
 #endif
         TS_TRY(lde_committed(c, c->stage[s], n, cols, b, shift_monty, dst + col0, cols, w));
 #ifndef TS_EMULATE
@@ -1086,6 +1175,15 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
 }
 
 // leaves_done: the leaf layer of t->digests was filled by the caller (pipelined commit: hash_rows_window)
+// Layers of at least 2^k children take tree_reduce3_kernel (three levels per launch, every lane busy: throughput), smaller ones
+// tree_reduce_kernel (eight levels per launch out of shared memory: fewer dependent launches).  Both are latency bound on small
+// layers (7 serial compressions per thread = 18.5 us against 8 barriers = 10.5 us), so the switch point decides how many
+// launches the small FRI rounds cost.  TS_TREE3_MIN_LOG overrides (A/B in profiles/r02/README.md).
+int tree3_min_log() {
+    if (const char *e = getenv("TS_TREE3_MIN_LOG")) return std::max(3, atoi(e));
+    return 14;
+}
+
 int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
     const size_t k = t->mats.size();
     size_t n_first = 0;
@@ -1136,7 +1234,7 @@ int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
             levels++;
         }
         const size_t n_ch = t->hmax >> (l - 1);
-        if (levels >= 3 && n_ch >= ((size_t)1 << 14) && getenv("TS_NO_TREE3") == nullptr) {
+        if (levels >= 3 && n_ch >= ((size_t)1 << tree3_min_log()) && getenv("TS_NO_TREE3") == nullptr) {
             // big layer: three levels per launch, one thread per 8 children
             KScope ks(c, TS_K_TREE);
             auto kfn3 = b3::tree_reduce3_kernel;
@@ -1265,15 +1363,15 @@ int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t
 }  // namespace
 
 // ================================================================================================ C ABI
-// A pageable host matrix is page-locked for the duration of a *_host call: the column-chunk pipeline issues strided 2-D
-// copies, which the driver stages row by row out of pageable memory (measured 5.9 GB/s on a 2^22 x 256 trace, 0.73 s per
-// commit) but runs at the PCIe rate out of registered memory.  A caller that keeps its trace for several calls registers it
-// once itself (ts_host_register) and skips this cost.
+// Pageable host matrices: the column-chunk pipeline stages them through page-locked bounce slots (stage_pageable_window).
+// Page-locking the caller's buffer for the duration of the call instead is opt-in (TS_AUTO_PIN=1): measured on a 2^22 x 256
+// trace it costs more than it saves (cudaHostRegister of 4 GiB ~ 1 s; commit 1.69 s against 0.73 s with the driver's own
+// row-by-row staging).  A caller that keeps its trace for several calls registers it once itself (ts_host_register).
 struct ScopedHostPin {
     const void *p = nullptr;
     ScopedHostPin(const void *host, size_t bytes) {
 #ifndef TS_EMULATE
-        if (!host || bytes < ((size_t)16 << 20) || getenv("TS_NO_AUTO_PIN")) return;
+        if (!host || bytes < ((size_t)16 << 20) || !getenv("TS_AUTO_PIN")) return;
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
             cudaGetLastError();
@@ -1448,6 +1546,16 @@ void ts_ctx_destroy(ts_ctx *c) {
             cudaEventDestroy(c->ev_free[s]);
         }
         cudaStreamDestroy(c->copy_stream);
+    }
+    if (c->bounce) {
+        for (int t = 0; t < ts_ctx::BOUNCE_WORKERS; t++) {
+            cudaStreamSynchronize(c->bounce_stream[t]);
+            cudaEventDestroy(c->bounce_ev[t][0]);
+            cudaEventDestroy(c->bounce_ev[t][1]);
+            cudaEventDestroy(c->bounce_done[t]);
+            cudaStreamDestroy(c->bounce_stream[t]);
+        }
+        cudaFreeHost(c->bounce);
     }
 #endif
     for (auto &kv : c->v4_post1) cudaFree(kv.second);
@@ -2378,7 +2486,12 @@ int ts_quotient_values(ts_ctx *c, const ts_matrix *trace_lde, unsigned log_n, un
     if (rc == TS_OK) {
         KScope ks(c, TS_K_MISC);
         auto kfn = quo::quotient_values_kernel;
-        TS_LAUNCH(kfn, (unsigned)((m + quo::QV_NT - 1) / quo::QV_NT), quo::QV_NT, (size_t)quo::MAX_REGS * quo::QV_NT * 4, c->stream, p);
+        // TS_QV_CTAS_PER_SM=k: k resident CTAs per SM walking the rows grid-stride (fewer rows in flight per L1); default one
+        // CTA per 128 rows
+        size_t grid = (m + 127) / 128;
+        if (const char *e = getenv("TS_QV_CTAS_PER_SM"))
+            if (atoi(e) > 0) grid = std::min(grid, (size_t)atoi(e) * (size_t)c->num_sms);
+        TS_LAUNCH(kfn, (unsigned)grid, 128, 0, c->stream, p);
         rc = check_launch(c, "quotient_values_kernel");
     }
     pool_release(c, dev);  // stream-ordered
@@ -2415,8 +2528,12 @@ int ts_interpolate_low_coset(ts_ctx *c, const ts_matrix *lde, size_t n, const ui
     if (log_n < 0 || log_h < 0 || n > lde->rows || inv_denoms->rows < n || inv_denoms->width != 4)
         TS_FAIL(c, TS_ERR_ARG, "interpolate_low_coset: bad sizes");
     const size_t w = lde->width, n_blocks = (n + opn::BARY_RB - 1) / opn::BARY_RB;
+    size_t n_ctas = std::min<size_t>(n_blocks, (size_t)c->num_sms * 4);
+    if (const char *e = getenv("TS_BARY_CTAS")) n_ctas = std::max<size_t>(1, std::min<size_t>(n_blocks, strtoul(e, nullptr, 10)));  // test hook
+    int tpr_log = 0;  // threads per row: the smallest power of two >= width, at most 256
+    while (tpr_log < 8 && ((size_t)1 << tpr_log) < w) tpr_log++;
     uint4 *partial = nullptr, *ys = nullptr;
-    TS_CUDA(c, pool_alloc(c, (void **)&partial, n_blocks * w * 16));
+    TS_CUDA(c, pool_alloc(c, (void **)&partial, n_ctas * w * 16));
     cudaError_t e = pool_alloc(c, (void **)&ys, w * 16);
     if (e != cudaSuccess) {
         pool_release(c, partial);
@@ -2427,14 +2544,14 @@ int ts_interpolate_low_coset(ts_ctx *c, const ts_matrix *lde, size_t n, const ui
         // the low coset of the committed LDE: rows r < n hold p(g * w_n^bitrev_n(r))
         KScope ks(c, TS_K_MISC);
         auto kfn = opn::bary_partial_kernel;
-        TS_LAUNCH(kfn, (unsigned)n_blocks, 256, (size_t)opn::BARY_RB * 16, c->stream, (const uint32_t *)lde->d, n, (uint32_t)w,
-                  log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial);
+        TS_LAUNCH(kfn, (unsigned)n_ctas, 256, (size_t)(opn::BARY_RB + 256) * 16, c->stream, (const uint32_t *)lde->d, n, (uint32_t)w,
+                  log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial, tpr_log);
         rc = check_launch(c, "bary_partial_kernel");
     }
     if (rc == TS_OK) {
         KScope ks(c, TS_K_MISC);
         auto kfn = opn::bary_final_kernel;
-        TS_LAUNCH(kfn, (unsigned)((w + 255) / 256), 256, 0, c->stream, (const uint4 *)partial, n_blocks, (uint32_t)w, ys);
+        TS_LAUNCH(kfn, (unsigned)((w + 31) / 32), 256, (size_t)256 * 16, c->stream, (const uint4 *)partial, n_ctas, (uint32_t)w, ys);
         rc = check_launch(c, "bary_final_kernel");
     }
     std::vector<uint32_t> s(w * 4);
@@ -3153,6 +3270,80 @@ int ts_taptree_commit(ts_ctx *c, const ts_matrix *leaf_rows, const uint8_t *segs
     if (rc != TS_OK) return fail(rc, nullptr);
     if (root) be_bytes(rw, root);
     *out = t;
+    return TS_OK;
+}
+int ts_padded_leaf_rows(ts_ctx *c, const ts_matrix *const *mats, size_t n_mats, ts_matrix **out) {
+    if (!c || !mats || !out || n_mats == 0 || n_mats > (size_t)b3::MAX_SEG) TS_FAIL(c, TS_ERR_ARG, "padded_leaf_rows: 1..32 matrices");
+    std::vector<size_t> order(n_mats);
+    for (size_t i = 0; i < n_mats; i++) {
+        order[i] = i;
+        if (!mats[i] || log2_strict(mats[i]->rows) < 0) TS_FAIL(c, TS_ERR_ARG, "padded_leaf_rows: heights must be powers of two");
+    }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return mats[a]->rows > mats[b]->rows; });  // tcs/mod.rs:346
+    const size_t hmax = mats[order[0]]->rows;
+    b3::Segments sg;
+    sg.n = (int)n_mats, sg.total_words = 0;
+    for (int i = 0; i < b3::MAX_SEG; i++) sg.ptr[i] = nullptr, sg.width[i] = 0xffffffffu, sg.shift[i] = 0;
+    for (size_t i = 0; i < n_mats; i++) {
+        const ts_matrix *m = mats[order[i]];
+        sg.ptr[i] = m->d, sg.width[i] = (uint32_t)m->width;
+        sg.shift[i] = (uint32_t)(log2_strict(hmax) - log2_strict(m->rows));
+        sg.total_words += (uint32_t)m->width;
+    }
+    if (sg.total_words == 0) TS_FAIL(c, TS_ERR_ARG, "padded_leaf_rows: empty rows");
+    ts_matrix *o = nullptr;
+    TS_TRY(new_matrix(c, hmax, sg.total_words, &o));
+    {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = b3::padded_rows_kernel;
+        const size_t total = hmax * sg.total_words;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream, sg, hmax, o->d);
+        const int rc = check_launch(c, "padded_rows_kernel");
+        if (rc != TS_OK) {
+            ts_matrix_free(o);
+            return rc;
+        }
+    }
+    *out = o;
+    return TS_OK;
+}
+int ts_taptree_open(ts_ctx *c, const ts_taptree *t, size_t index, uint8_t *path_out, uint32_t *position_out) {
+    if (!c || !t || index >= t->n_leaves || (t->log_n && !path_out)) TS_FAIL(c, TS_ERR_ARG, "taptree_open: bad argument");
+    // TapBranch hashes are symmetric in their children, so the branch of Merkle leaf m is its siblings in construction order
+    // (complete_taptree.rs:34-49: the TaprootMerkleBranch of leaf_indices[m]), leaf level first
+    std::vector<opn::GatherSeg> segs;
+    size_t off = 0;
+    for (unsigned l = 0; l < t->log_n; l++) {
+        segs.push_back({t->nodes + (off + ((index >> l) ^ 1)) * 8, (uint32_t)(8 * l), 8u});
+        off += t->n_leaves >> l;
+    }
+    segs.push_back({t->leaf_idx + index, (uint32_t)(8 * t->log_n), 1u});
+    opn::GatherSeg *dsegs = nullptr;
+    uint32_t *dbuf = nullptr;
+    const size_t words = 8 * (size_t)t->log_n + 1;
+    TS_CUDA(c, pool_alloc(c, (void **)&dsegs, segs.size() * sizeof(opn::GatherSeg)));
+    cudaError_t e = pool_alloc(c, (void **)&dbuf, words * 4);
+    if (e != cudaSuccess) {
+        pool_release(c, dsegs);
+        TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    std::vector<uint32_t> host(words);
+    int rc = TS_OK;
+    e = cudaMemcpyAsync(dsegs, segs.data(), segs.size() * sizeof(opn::GatherSeg), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        KScope ks(c, TS_K_MISC);
+        auto kfn = opn::gather_segments_kernel;
+        TS_LAUNCH(kfn, (unsigned)segs.size(), 32, 0, c->stream, (const opn::GatherSeg *)dsegs, (uint32_t)segs.size(), dbuf);
+        rc = check_launch(c, "gather_segments_kernel");
+    }
+    if (e == cudaSuccess && rc == TS_OK) e = cudaMemcpyAsync(host.data(), dbuf, words * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && rc == TS_OK) e = cudaStreamSynchronize(c->stream);
+    pool_release(c, dsegs);
+    pool_release(c, dbuf);
+    if (e != cudaSuccess) TS_FAIL(c, TS_ERR_CUDA, cudaGetErrorString(e));
+    if (rc != TS_OK) return rc;
+    for (unsigned l = 0; l < t->log_n; l++) be_bytes(&host[8 * l], path_out + 32 * l);
+    if (position_out) *position_out = host[8 * t->log_n];
     return TS_OK;
 }
 int ts_taptree_leaf_indices(ts_ctx *c, const ts_taptree *t, uint32_t *out_host) {

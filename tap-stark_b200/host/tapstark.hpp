@@ -231,6 +231,65 @@ private:
     int layout_;
 };
 
+// The commitment TapTreeMmcs computes (basic/src/tcs/mod.rs:238-282) over a script template; the template (bit-commitment locking
+// scripts around pushed integers) is host work of the caller, as the key generation is in the reference.
+struct ScriptTemplate {
+    std::vector<std::vector<uint8_t>> segments;  // n_push + 1 constant byte runs
+    std::vector<uint32_t> push_word;             // word of the leaf row behind push k + 1 (push 0 is the leaf index)
+};
+class TapTree {
+public:
+    // PolyTCS::padding_matrix on the device: the rows the leaves commit to when matrices of several heights share a tree
+    static DeviceMatrix padded_rows(const Context &c, const std::vector<const DeviceMatrix *> &mats) {
+        std::vector<const ts_matrix *> raw;
+        for (auto *m : mats) raw.push_back(m->raw());
+        ts_matrix *o = nullptr;
+        c.check(ts_padded_leaf_rows(c.raw(), raw.data(), raw.size(), &o), "padded_leaf_rows");
+        return DeviceMatrix(c, o);
+    }
+    TapTree(const Context &c, const DeviceMatrix &leaf_rows, const ScriptTemplate &tpl) : c_(&c) {
+        if (tpl.segments.size() != tpl.push_word.size() + 2) throw Panic("taptree: need one segment more than pushes");
+        std::vector<uint8_t> blob;
+        std::vector<size_t> off{0};
+        for (auto &sgm : tpl.segments) {
+            blob.insert(blob.end(), sgm.begin(), sgm.end());
+            off.push_back(blob.size());
+        }
+        c.check(ts_taptree_commit(c.raw(), leaf_rows.raw(), blob.data(), off.data(), tpl.push_word.data(), tpl.push_word.size() + 1,
+                                  root_.data(), &t_), "taptree_commit");
+        n_leaves_ = leaf_rows.height();
+    }
+    TapTree(TapTree &&o) noexcept : c_(o.c_), t_(o.t_), root_(o.root_), n_leaves_(o.n_leaves_) { o.t_ = nullptr; }
+    TapTree(const TapTree &) = delete;
+    ~TapTree() {
+        if (t_) ts_taptree_free(t_);
+    }
+    const Digest &root() const { return root_; }
+    // CompleteTaptree::leaf_indices (reverse_idx_dict, builder.rs:96-102)
+    std::vector<uint32_t> leaf_indices() const {
+        std::vector<uint32_t> v(n_leaves_);
+        c_->check(ts_taptree_leaf_indices(c_->raw(), t_, v.data()), "taptree_leaf_indices");
+        return v;
+    }
+    // (TaprootMerkleBranch of Merkle leaf `index`, its position among the TapTree's leaves)
+    std::pair<std::vector<Digest>, uint32_t> open(size_t index) const {
+        size_t depth = 0;
+        while (((size_t)1 << depth) < n_leaves_) depth++;
+        std::vector<uint8_t> path(32 * (depth ? depth : 1));
+        uint32_t pos = 0;
+        c_->check(ts_taptree_open(c_->raw(), t_, index, path.data(), &pos), "taptree_open");
+        std::vector<Digest> br(depth);
+        for (size_t l = 0; l < depth; l++) std::copy(path.begin() + 32 * l, path.begin() + 32 * l + 32, br[l].begin());
+        return {br, pos};
+    }
+
+private:
+    const Context *c_;
+    ts_taptree *t_ = nullptr;
+    Digest root_{};
+    size_t n_leaves_ = 0;
+};
+
 // BfChallenger<Challenge, U32, Blake3Permutation, 16>
 class BfChallenger {
 public:

@@ -48,6 +48,7 @@ pub mod sys {
     #[repr(C)] pub struct ts_matrix { _p: [u8; 0] }
     #[repr(C)] pub struct ts_tree { _p: [u8; 0] }
     #[repr(C)] pub struct ts_challenger { _p: [u8; 0] }
+    #[repr(C)] pub struct ts_taptree { _p: [u8; 0] }
     extern "C" {
         pub fn ts_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut ts_ctx) -> c_int;
         pub fn ts_ctx_destroy(ctx: *mut ts_ctx);
@@ -103,6 +104,15 @@ pub mod sys {
         pub fn ts_challenger_sample_bits(c: *mut ts_challenger, bits: c_uint, ext: c_int) -> usize;
         pub fn ts_challenger_check_witness(c: *mut ts_challenger, bits: c_uint, witness: u32, ext: c_int) -> c_int;
         pub fn ts_challenger_grind(c: *mut ts_challenger, bits: c_uint, ext: c_int, witness: *mut u32) -> c_int;
+        // TapTree commitment (basic/src/tcs): leaf scripts from a template, sorted-pair TapBranch tree
+        pub fn ts_matrix_from_host(ctx: *mut ts_ctx, host: *const u32, rows: usize, width: usize, out: *mut *mut ts_matrix) -> c_int;
+        pub fn ts_matrix_free(m: *mut ts_matrix);
+        pub fn ts_padded_leaf_rows(ctx: *mut ts_ctx, mats: *const *const ts_matrix, n_mats: usize, out: *mut *mut ts_matrix) -> c_int;
+        pub fn ts_taptree_commit(ctx: *mut ts_ctx, leaf_rows: *const ts_matrix, segs: *const u8, seg_offsets: *const usize,
+                                 push_word: *const u32, n_push: usize, root: *mut u8, out: *mut *mut ts_taptree) -> c_int;
+        pub fn ts_taptree_leaf_indices(ctx: *mut ts_ctx, t: *const ts_taptree, out_host: *mut u32) -> c_int;
+        pub fn ts_taptree_open(ctx: *mut ts_ctx, t: *const ts_taptree, index: usize, path_out: *mut u8, position_out: *mut u32) -> c_int;
+        pub fn ts_taptree_free(t: *mut ts_taptree);
     }
 }
 
@@ -598,4 +608,59 @@ pub fn fold_even_odd(poly: Vec<Challenge>, beta: Challenge) -> Vec<Challenge> {
     });
     unsafe { out.set_len(h) };
     out
+}
+
+// ------------------------------------------------------------------------------------------------ TapTree commitment
+/// The device side of `TCS::commit_polys` (basic/src/tcs/mod.rs:238-282): `CompleteTaptree::new_with_scripts` over leaf scripts that
+/// share their bit-commitment locking scripts.  The caller passes the script as a template -- the `n + 1` constant byte runs around
+/// the `n` pushed integers (`{self.index}` first, then the evaluation limbs in `generate_script`'s order, tcs/mod.rs:197-225) -- and
+/// which word of the padded leaf row each later push takes; nothing per leaf is built on the host.
+pub struct GpuTapTree {
+    raw: *mut sys::ts_taptree,
+    pub root: [u8; 32],
+    pub n_leaves: usize,
+}
+impl Drop for GpuTapTree { fn drop(&mut self) { unsafe { sys::ts_taptree_free(self.raw) } } }
+impl GpuTapTree {
+    /// `matrices`: Montgomery words as p3 stores them; the padded rows (`PolyTCS::padding_matrix`) are built on the device.
+    pub fn commit(matrices: &[RowMajorMatrix<BabyBear>], segments: &[Vec<u8>], push_word: &[u32]) -> Self {
+        assert_eq!(segments.len(), push_word.len() + 2, "one segment more than pushes");
+        CTX.with(|c| {
+            let mut devs: Vec<*mut sys::ts_matrix> = Vec::with_capacity(matrices.len());
+            for m in matrices {
+                let mut d = std::ptr::null_mut();
+                let rc = unsafe { sys::ts_matrix_from_host(c.0, m.values.as_ptr() as *const u32, m.height(), m.width(), &mut d) };
+                c.check(rc, "ts_matrix_from_host");
+                devs.push(d);
+            }
+            let consts: Vec<*const sys::ts_matrix> = devs.iter().map(|d| *d as *const _).collect();
+            let mut rows = std::ptr::null_mut();
+            let rc = unsafe { sys::ts_padded_leaf_rows(c.0, consts.as_ptr(), consts.len(), &mut rows) };
+            c.check(rc, "ts_padded_leaf_rows");
+            let blob: Vec<u8> = segments.concat();
+            let mut offs = vec![0usize];
+            for s in segments { offs.push(offs.last().unwrap() + s.len()); }
+            let (mut root, mut raw) = ([0u8; 32], std::ptr::null_mut());
+            let rc = unsafe { sys::ts_taptree_commit(c.0, rows, blob.as_ptr(), offs.as_ptr(), push_word.as_ptr(), push_word.len() + 1,
+                                                     root.as_mut_ptr(), &mut raw) };
+            let n_leaves = matrices.iter().map(|m| m.height()).max().unwrap_or(0);
+            unsafe { sys::ts_matrix_free(rows); for d in devs { sys::ts_matrix_free(d); } }
+            c.check(rc, "ts_taptree_commit");
+            GpuTapTree { raw, root, n_leaves }
+        })
+    }
+    /// `CompleteTaptree::leaf_indices` (reverse_idx_dict, builder.rs:96-102).
+    pub fn leaf_indices(&self) -> Vec<u32> {
+        let mut v = vec![0u32; self.n_leaves];
+        CTX.with(|c| c.check(unsafe { sys::ts_taptree_leaf_indices(c.0, self.raw, v.as_mut_ptr()) }, "ts_taptree_leaf_indices"));
+        v
+    }
+    /// The `TaprootMerkleBranch` of Merkle leaf `index` (leaf level first) and its TapTree position (tcs/mod.rs:141-146).
+    pub fn open(&self, index: usize) -> (Vec<[u8; 32]>, u32) {
+        let depth = self.n_leaves.trailing_zeros() as usize;
+        let mut path = vec![0u8; 32 * depth.max(1)];
+        let mut pos = 0u32;
+        CTX.with(|c| c.check(unsafe { sys::ts_taptree_open(c.0, self.raw, index, path.as_mut_ptr(), &mut pos) }, "ts_taptree_open"));
+        ((0..depth).map(|l| path[32 * l..32 * l + 32].try_into().unwrap()).collect(), pos)
+    }
 }

@@ -4,6 +4,7 @@
 //   commit_single / commit_many  fri/tests/pcs.rs:70-110 (commit side: round shapes of the reference's cases)
 //   mmcs commit/open/verify      basic/src/mmcs/taptree_mmcs.rs tests (commit -> open_batch -> verify_batch, tamper)
 //   commit phase                 fri/tests/fri.rs:50-130 (LDE -> bit-reverse -> bf_commit_phase)
+//   taptree                      basic/src/tcs/mod.rs tests (commit -> open -> verify_inclusion), padding_matrix
 //   pcs open                     fri/tests/pcs.rs:70-110 (commit -> sample zeta -> open; the verifier-side checks that need
 //                                only the oracle's field arithmetic are replayed: opened values, Merkle openings, fold chain)
 // The same binary links the CUDA library (pytest -m gpu) or the emulated build of the same kernel sources.
@@ -370,6 +371,74 @@ static void test_pcs_open(const Context &ctx) {
     CHECK(panicked);
 }
 
+// TapTree (basic/src/tcs/mod.rs:238-301): commit over a script template, open, verify_inclusion (complete_taptree.rs:64-73) with
+// the oracle's tagged SHA-256; the padded rows against the oracle's padding_matrix.
+static std::vector<uint8_t> push_num(uint32_t v) {  // minimal script-number push of a non-negative integer
+    if (v == 0) return {0x00};
+    if (v <= 16) return {(uint8_t)(0x50 + v)};
+    std::vector<uint8_t> b;
+    for (uint32_t a = v; a; a >>= 8) b.push_back((uint8_t)a);
+    if (b.back() & 0x80) b.push_back(0);
+    b.insert(b.begin(), (uint8_t)b.size());
+    return b;
+}
+static void test_taptree(const Context &ctx) {
+    const size_t heights[3] = {32, 8, 32}, widths[3] = {2, 3, 1};
+    std::vector<std::vector<uint32_t>> host;
+    std::vector<DeviceMatrix> mats;
+    const uint32_t *ptrs[3];
+    for (int i = 0; i < 3; i++) {
+        host.push_back(rand_canonical(heights[i] * widths[i]));
+        if (i == 0) host[0][0] = 0, host[0][1] = 16, host[0][2] = 128, host[0][3] = 0x77ffffff;  // every push length
+        mats.emplace_back(ctx, RowMajorMatrix<Val>(monty(host[i]), widths[i]));
+    }
+    for (int i = 0; i < 3; i++) ptrs[i] = host[i].data();
+    DeviceMatrix rows = TapTree::padded_rows(ctx, {&mats[0], &mats[1], &mats[2]});
+    CHECK(rows.height() == 32 && rows.width() == 6);
+    const std::vector<uint32_t> got_rows = canon(rows.to_row_major_matrix().values);
+    for (size_t leaf = 0; leaf < 32; leaf++) {
+        uint32_t want[6];
+        CHECK(or_padded_leaf(ptrs, heights, widths, 3, leaf, want) == 6);
+        CHECK(std::memcmp(want, &got_rows[6 * leaf], 24) == 0);
+    }
+    // a template shaped like generate_script (tcs/mod.rs:197-225): opaque "locking script" bytes around the pushes, > 252 bytes in
+    // total so the compact-size length takes three bytes
+    ScriptTemplate tpl;
+    for (size_t k = 0; k <= 7; k++) {
+        std::vector<uint8_t> seg(k == 0 ? 300 : 41 + k);
+        for (auto &b : seg) b = (uint8_t)next_u64();
+        tpl.segments.push_back(seg);
+    }
+    tpl.push_word = {0, 1, 5, 4, 3, 2};
+    TapTree tree(ctx, rows, tpl);
+    const auto perm = tree.leaf_indices();
+    std::vector<bool> seen(32, false);
+    for (uint32_t p : perm) {
+        CHECK(p < 32 && !seen[p]);
+        seen[p] = true;
+    }
+    for (size_t index : {0u, 1u, 13u, 31u}) {
+        std::vector<uint8_t> script(tpl.segments[0]);
+        auto num = push_num((uint32_t)index);
+        script.insert(script.end(), num.begin(), num.end());
+        for (size_t k = 0; k < tpl.push_word.size(); k++) {
+            script.insert(script.end(), tpl.segments[k + 1].begin(), tpl.segments[k + 1].end());
+            num = push_num(got_rows[6 * index + tpl.push_word[k]]);
+            script.insert(script.end(), num.begin(), num.end());
+        }
+        script.insert(script.end(), tpl.segments.back().begin(), tpl.segments.back().end());
+        uint8_t h[32], nx[32];
+        or_tap_leaf_hash(script.data(), script.size(), h);
+        auto [branch, pos] = tree.open(index);
+        CHECK(branch.size() == 5 && pos == perm[index]);
+        for (auto &sib : branch) {
+            or_tap_branch_hash(h, sib.data(), nx);
+            std::memcpy(h, nx, 32);
+        }
+        CHECK(std::memcmp(h, tree.root().data(), 32) == 0);
+    }
+}
+
 int main() {
     Context ctx(0);
     run("dft_roundtrip_and_oracle", [&] { test_dft_roundtrip_and_oracle(ctx); });
@@ -382,6 +451,7 @@ int main() {
     run("pcs_commit_many_different", [&] { do_test_pcs_commit(ctx, {{3, 4}, {6, 9}, {4, 1}, {6, 2}}, 1); });
     run("commit_phase", [&] { test_commit_phase(ctx); });
     run("pcs_open", [&] { test_pcs_open(ctx); });
+    run("taptree", [&] { test_taptree(ctx); });
     std::printf("%d passed, %d failed\n", passed, failures);
     return failures ? 1 : 0;
 }

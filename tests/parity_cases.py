@@ -189,6 +189,47 @@ def check_dot_ext_powers(ts, ctx, orc, rows, width, seed=8):
     assert np.array_equal(got, acc.astype(np.uint32))
 
 
+# ---- interpolate_coset (fri/src/two_adic_pcs.rs:358-369) --------------------------------------------------------
+def check_interpolate_low_coset(ts, ctx, orc, log_n, width, log_blowup, seed=60):
+    """p_c(z) from the low coset of a committed LDE == sum_k coeff[k][c] z^k (coefficients from the oracle's inverse DFT)."""
+    import ctypes as C
+
+    n = 1 << log_n
+    ev = rand_mat(seed, n, width)
+    z = rand_mat(seed + 1, 1, 4)[0]
+    coeffs = orc.idft_batch(ev).astype(np.uint64)          # p on H_n, natural order -> coefficients
+    zpow = np.zeros((n, 4), dtype=np.uint64)                # z^k by doubling
+    zpow[0, 0] = 1
+    m, zm_ = 1, z.astype(np.uint32)
+    while m < n:
+        # zpow[m:2m] = zpow[0:m] * z^m, vectorised extension-field product
+        a, b = zpow[:m], zm_.astype(np.uint64)
+        out = np.zeros((m, 4), dtype=np.uint64)
+        for i in range(4):
+            for j in range(4):
+                t = (a[:, i] * b[j]) % P
+                if i + j >= 4:
+                    t = (t * 11) % P
+                out[:, (i + j) % 4] = (out[:, (i + j) % 4] + t) % P
+        zpow[m : 2 * m] = out
+        zm_ = orc.ef_mul(zm_, zm_)
+        m *= 2
+    want = np.zeros((width, 4), dtype=np.uint32)
+    for k in range(4):
+        want[:, k] = ((coeffs * zpow[:, k : k + 1]) % P).sum(axis=0) % P
+    dm = ts.DeviceMatrix.from_canonical(ctx, ev)
+    lde = ts.GpuDft(ctx).coset_lde_batch(dm, log_blowup, 31, committed_order=True)  # committed order, shift g (two_adic_pcs.rs:235-243)
+    L = ts.lib()
+    zmont = ts.to_monty(z)
+    h = C.c_void_p()
+    ctx.check(L.ts_inv_denoms(ctx._h, log_n + log_blowup, zmont.ctypes.data_as(C.c_void_p), C.byref(h)), "inv_denoms")
+    inv = ts.DeviceMatrix(ctx, h)
+    ys = np.empty((width, 4), dtype=np.uint32)
+    ctx.check(L.ts_interpolate_low_coset(ctx._h, lde._h, n, zmont.ctypes.data_as(C.c_void_p), inv._h,
+                                         ys.ctypes.data_as(C.c_void_p)), "interpolate_low_coset")
+    assert np.array_equal(ts.from_monty(ys), want)
+
+
 # ---- Pcs::open + verify (fri/src/two_adic_pcs.rs:260-530, fri/src/prover.rs, fri/src/verifier.rs) ------------------
 def check_pcs_open_verify(ts, ctx, orc, round_shapes, log_blowup, num_queries=6, pow_bits=4, seed=70):
     """round_shapes: [[(log_n, width, n_points)] per commit round].  The device `open` must (1) return the

@@ -34,7 +34,7 @@ def _build_and_run(lib: Path, name: str):
 def test_host_mirror_emulated():
     from emul import build_emul
     out = _build_and_run(build_emul.build(), "host_mirror_emul")
-    assert "10 passed" in out
+    assert "11 passed" in out
 
 
 @pytest.mark.gpu
@@ -42,4 +42,4 @@ def test_host_mirror_gpu():
     lib = ROOT / "tap-stark_b200" / "libtapstark_b200.so"
     assert lib.exists(), "CUDA library not built: run __graft_entry__.build()"
     out = _build_and_run(lib, "host_mirror_gpu")
-    assert "10 passed" in out
+    assert "11 passed" in out

@@ -205,6 +205,14 @@ def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 33, 256)
 
 
+@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1)])
+def test_interpolate_low_coset(ts, ctx, orc, monkeypatch, log_n, width, ctas):
+    """Row-lane mapping for narrow matrices, one lane for wide ones, column groups past 256, grid-stride row blocks."""
+    if ctas is not None:
+        monkeypatch.setenv("TS_BARY_CTAS", str(ctas))
+    pc.check_interpolate_low_coset(ts, ctx, orc, log_n, width, 1, seed=60 + width)
+
+
 def test_pcs_open_verify(ts, ctx, orc):
     # uni-stark shape (uni-stark/src/prover.rs:94-104): trace opened at zeta and zeta*w, quotient chunks at zeta
     pc.check_pcs_open_verify(ts, ctx, orc, [[(5, 3, 2)], [(5, 4, 1), (5, 4, 1)]], 2)

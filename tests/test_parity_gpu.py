@@ -238,9 +238,17 @@ def test_pcs_commit_host_pipelined(ts, ctx, orc, width):
     mm = ts.Blake3MerkleMmcs(ctx)
     pcs = ts.TwoAdicFriPcs(ts.GpuDft(ctx), mm, ts.FriConfig(1, 2, 8, mm))
     dom = pcs.natural_domain_for_degree(1 << 18)
-    root_h, data_h = pcs.commit_host([(dom, ts.to_monty(ev))])
+    ev_m = ts.to_monty(ev)
+    root_h, data_h = pcs.commit_host([(dom, ev_m)])  # pageable source: gathered through the page-locked bounce slots
     root_d, _ = pcs.commit([(dom, ts.DeviceMatrix.from_canonical(ctx, ev))])
     assert root_h == root_d
+    L = ts.lib()
+    ctx.check(L.ts_host_register(ctx._h, ev_m.ctypes.data, ev_m.nbytes), "host_register")
+    try:
+        root_p, _ = pcs.commit_host([(dom, ev_m)])  # page-locked source: strided 2-D copies straight from the caller's rows
+    finally:
+        ctx.check(L.ts_host_unregister(ctx._h, ev_m.ctypes.data), "host_unregister")
+    assert root_p == root_d
     cols = [0, 63, 64, width - 1]
     lde = mm.get_matrices(data_h)[0].to_canonical()
     assert np.array_equal(lde[:, cols], orc.pcs_lde_committed(np.ascontiguousarray(ev[:, cols]), 1))
@@ -425,6 +433,15 @@ def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
         return
     # replay: betas from the commitments, then fold_row along the path of one index using opened layer rows
     _replay_query_path(ts, orc, cfg, res, log_len, 987654321 % (1 << log_len))
+
+
+@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1),
+                                              (18, 4, None), (17, 200, None)])
+def test_interpolate_low_coset(ts, ctx, orc, monkeypatch, log_n, width, ctas):
+    """interpolate_coset on the device against sum_k c_k z^k; the last two shapes have more row blocks than CTAs."""
+    if ctas is not None:
+        monkeypatch.setenv("TS_BARY_CTAS", str(ctas))
+    pc.check_interpolate_low_coset(ts, ctx, orc, log_n, width, 1, seed=60 + width)
 
 
 def test_pcs_open_verify(ts, ctx, orc):
