@@ -312,8 +312,8 @@ def run_b200(a):
                "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e}
         runner.release_host()
         if world == 1 and hasattr(runner, "prepare_host"):
-            # the same call on a PAGEABLE host trace (a Rust Vec that was not registered with ts_host_register): the driver
-            # stages the copy through its own pinned buffers
+            # the same call on a PAGEABLE host trace (a Rust Vec that was not registered with ts_host_register): the library
+            # gathers the column windows into page-locked bounce slots with host threads (tapstark.cu: stage_pageable_window)
             try:
                 runner.prepare_host(pinned=False)
                 runner.step_e2e()

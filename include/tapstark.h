@@ -119,7 +119,9 @@ int ts_coset_lde_batch_host(ts_ctx *ctx, const uint32_t *evals_host, size_t rows
 int ts_dft_batch_host(ts_ctx *ctx, int kind, const uint32_t *mat_host, size_t rows, size_t width, uint32_t shift_monty,
                       uint32_t *out_host);
 /* Page-lock / unlock a caller-owned host buffer (a Rust Vec<BabyBear> the prover keeps for the whole proof): the *_host
- * entry points then copy it at the PCIe rate instead of the driver's pageable staging rate.  Optional. */
+ * entry points then copy its column windows straight out of the caller's rows at the PCIe rate.  Optional: a pageable
+ * source is gathered by host threads into page-locked bounce slots inside the call (measured 132 ms against 91 ms for a
+ * 2^22 x 256 commit; page-locking the buffer per call would cost ~1 s). */
 int ts_host_register(ts_ctx *ctx, const void *host, size_t bytes);
 int ts_host_unregister(ts_ctx *ctx, const void *host);
 
@@ -378,6 +380,12 @@ int ts_fri_chain_end(ts_ctx *ctx, uint32_t *chain_dev, ts_challenger *chal, size
  * addend_dev (may be NULL) is the matching slice of the next FRI input. */
 int ts_fri_fold_ext_shard(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev);
+/* The same fold that also emits the leaf digests of the NEXT commit-phase round (fri/src/prover.rs:112-113: the folded vector
+ * viewed as rows of two extension elements, hashed as canonical little-endian words): next_digests_dev = (h_local / 2) x 8 words.
+ * The layer is then not read a second time by a leaf-hash pass.  h_global >= 512; first and h_local multiples of 512. */
+int ts_fri_fold_hash_shard(ts_ctx *ctx, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev,
+                           uint32_t *next_digests_dev);
 /* plain Blake3 on the host: compress the G sub-roots into the root (and what the verifier side uses) */
 void ts_blake3_host(const uint8_t *in, size_t len, uint8_t out[32]);
 

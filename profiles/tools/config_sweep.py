@@ -139,6 +139,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "open":
         open_c4()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fri":
+        fri_sweep()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fold":
         fold_rates()
         sys.exit(0)

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "ts_ipc_close": (C.c_int, [_vp, _vp]),
     "ts_quotient_values": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ts_fri_fold_ext_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp]),
+    "ts_fri_fold_hash_shard": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp]),
     "ts_blake3_host": (None, [_vp, C.c_size_t, _vp]),
     "ts_pcs_open": (C.c_int, [_vp, _vpp, C.c_size_t, _szp, _vp, C.c_uint, C.c_uint, C.c_uint, _vp, _vpp, _szp]),
     "ts_bytes_free": (None, [_vp]),

@@ -11,6 +11,7 @@
 // with no other global traffic.
 #pragma once
 #include "field.cuh"
+#include "hash.cuh"
 
 namespace fold {
 
@@ -89,6 +90,63 @@ __global__ void __launch_bounds__(FOLD_T) fold_ext_kernel(const uint4 *__restric
     }
 }
 
+// Fold + the NEXT round's leaf hashes in one pass (fri/src/prover.rs:110-126): the next round commits to the folded vector viewed
+// as rows of two extension elements (prover.rs:112), i.e. leaf j = Blake3(out[2j] || out[2j+1]) as canonical little-endian words.
+// A thread folds the two neighbouring rows 2j and 2j+1 and hashes what it just produced, so the layer is not read a second time
+// by a leaf-hash kernel (and one dependent launch per round disappears).  Twiddles: g_inv^bitrev(2j) = T9[j mod 256] * T_hi(j div
+// 256) with T9[t] = (w_1024^-1)^bitrev8(t) raised per thread once, g_inv^bitrev(2j+1) = g_inv^bitrev(2j) * g_inv^(h/2).
+// Requires log_h >= 9; dl holds the chunk deltas of (log_h - 9)-bit chunk indices.  digests: h_local/2 x 8 words.
+// Row-sharded use as fold_ext_kernel: rows [first, first + h_local) of the layer, both multiples of 512; in/out/addend/digests
+// point at the shard.
+__global__ void __launch_bounds__(FOLD_T) fold_hash_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                           const uint4 *__restrict__ addend, int log_h, size_t first,
+                                                           size_t h_local, ef::E4 half_beta, InvRootPows rp, ChunkDeltas dl,
+                                                           const uint32_t *__restrict__ half_beta_dev,
+                                                           uint32_t *__restrict__ digests) {
+    if (half_beta_dev) {
+        TS_UNROLL
+        for (int i = 0; i < 4; i++) half_beta.c[i] = half_beta_dev[i];
+    }
+    const ef::E4Const hb = ef::prepare(half_beta);
+    const size_t chunks = h_local >> 9, cpb = (chunks + gridDim.x - 1) / gridDim.x, chunk_first = first >> 9;
+    const size_t c0 = (size_t)blockIdx.x * cpb, c1 = c0 + cpb < chunks ? c0 + cpb : chunks;
+    if (c0 >= c1) return;
+    const uint32_t t_lo = pow_from_table(rp, brev_bits(threadIdx.x, 8) << (log_h - 9));
+    const uint32_t w4_inv = rp.v[log_h - 1];  // g_inv^(h/2)
+    uint32_t t_hi = pow_from_table(rp, brev_bits((uint32_t)(c0 + chunk_first), log_h - 9));
+    for (size_t c = c0; c < c1; c++) {
+        const size_t j = (c << 8) + threadIdx.x;
+        const uint32_t s0 = bb::mmul(t_lo, t_hi), s1 = bb::mmul(s0, w4_inv);
+        uint32_t m[16];
+        TS_UNROLL
+        for (int k = 0; k < 2; k++) {
+            const uint4 a = in[4 * j + 2 * k], b = in[4 * j + 2 * k + 1];
+            ef::E4 lo{{a.x, a.y, a.z, a.w}}, hi{{b.x, b.y, b.z, b.w}};
+            const ef::E4 sum = ef::half(ef::add(lo, hi));
+            const ef::E4 dif = ef::scale(ef::sub(lo, hi), k ? s1 : s0);
+            ef::E4 r = ef::add(sum, ef::mul(dif, hb));
+            if (addend) {
+                const uint4 x = addend[2 * j + k];
+                r = ef::add(r, ef::E4{{x.x, x.y, x.z, x.w}});
+            }
+            out[2 * j + k] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
+            TS_UNROLL
+            for (int i = 0; i < 4; i++) m[4 * k + i] = bb::from_monty(r.c[i]);
+        }
+        TS_UNROLL
+        for (int i = 8; i < 16; i++) m[i] = 0;
+        uint32_t cv[8];
+        b3::iv(cv);
+        b3::compress(cv, m, 0, 32u, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
+        uint4 *d = reinterpret_cast<uint4 *>(digests) + 2 * j;
+        d[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+        d[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+        int t = 0;
+        for (size_t cc = c + chunk_first; cc & 1; cc >>= 1) t++;
+        t_hi = bb::mmul(t_hi, dl.v[t < 27 ? t : 27]);
+    }
+}
+
 // Base-field fold (the reference's own fold test and fri/tests/fri.rs run FRI over BabyBear itself).
 __global__ void __launch_bounds__(FOLD_T) fold_base_kernel(const uint2 *__restrict__ in, uint32_t *__restrict__ out,
                                                            int log_h, uint32_t half_beta, InvRootPows rp) {
@@ -158,6 +216,44 @@ __global__ void __launch_bounds__(256) dot_ext_powers_kernel(const uint32_t *__r
 TS_D uint64_t fold64(uint64_t t) {
     const uint32_t hi = (uint32_t)(t >> 32);
     return ((uint64_t)bb::umin32(hi, hi - bb::P) << 32) | (uint32_t)t;
+}
+
+// Rows of 4 or 8 words (quotient chunks, fri/src/two_adic_pcs.rs:375 on a BabyBear^4 column flattened to base-field columns):
+// one thread per row, the row in one or two 16-byte loads, grid-stride.  The warp-transposing kernel below moves 16 of every 64
+// staged bytes for such rows (measured 1.4 TB/s on 2^23 x 4).
+__global__ void __launch_bounds__(256) dot_rows_small_kernel(const uint4 *__restrict__ m, size_t rows, uint32_t quads,
+                                                             const uint4 *__restrict__ apow, uint4 *__restrict__ out,
+                                                             int accumulate) {
+    uint4 a[8];
+    TS_UNROLL
+    for (int i = 0; i < 8; i++) a[i] = (uint32_t)i < 4 * quads ? apow[i] : make_uint4(0, 0, 0, 0);
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+        uint64_t acc[4] = {0, 0, 0, 0};
+        TS_UNROLL
+        for (int q = 0; q < 2; q++) {
+            if ((uint32_t)q < quads) {
+                const uint4 v = m[r * quads + q];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                TS_UNROLL
+                for (int i = 0; i < 4; i += 2) {
+                    const uint4 a0 = a[4 * q + i], a1 = a[4 * q + i + 1];
+                    acc[0] = fold64(acc[0] + (uint64_t)w[i] * a0.x + (uint64_t)w[i + 1] * a1.x);
+                    acc[1] = fold64(acc[1] + (uint64_t)w[i] * a0.y + (uint64_t)w[i + 1] * a1.y);
+                    acc[2] = fold64(acc[2] + (uint64_t)w[i] * a0.z + (uint64_t)w[i + 1] * a1.z);
+                    acc[3] = fold64(acc[3] + (uint64_t)w[i] * a0.w + (uint64_t)w[i + 1] * a1.w);
+                }
+            }
+        }
+        uint32_t o[4];
+        TS_UNROLL
+        for (int k = 0; k < 4; k++) o[k] = bb::redc(acc[k]);
+        if (accumulate) {
+            const uint4 prev = out[r];
+            o[0] = bb::add(o[0], prev.x); o[1] = bb::add(o[1], prev.y);
+            o[2] = bb::add(o[2], prev.z); o[3] = bb::add(o[3], prev.w);
+        }
+        out[r] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // Hot path of dot_ext_powers for matrices with width % 4 == 0 (the committed LDE): a warp owns 32 rows; per block

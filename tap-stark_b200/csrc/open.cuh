@@ -54,18 +54,65 @@ TS_D ef::E4 ef_inv(const ef::E4 &a) {
 }
 TS_D ef::E4 ef_mul_full(const ef::E4 &a, const ef::E4 &b) { return ef::mul(a, ef::prepare(b)); }
 
-// out[X] = 1 / (g * w_h^bitrev(X) - z)
+// out[X] = 1 / (g * w_h^bitrev(X) - z).
+// Only the constant coefficient of the denominator depends on X, so the norm to F_p of a0 + a1 x + a2 x^2 + a3 x^3 (through
+// F_p[y]/(y^2 - W): n0 + n1 y with n0 = a0^2 + C0, n1 = a0 C1 - C2) costs five multiplications per point; a thread takes the eight
+// points X = j h/8 + t (bitrev(X) = 8 bitrev(t) + bitrev3(j): one table power per thread, coalesced stores across t) and inverts
+// their norms with ONE field inversion (Montgomery's trick).  About 30 multiplications per point instead of 105.
 __global__ void __launch_bounds__(256) inv_denoms_kernel(uint4 *out, int log_h, uint32_t g_monty, RootPows rp, ef::E4 z) {
+    using bb::add;
+    using bb::mmul;
+    using bb::neg;
+    using bb::sub;
     const size_t h = (size_t)1 << log_h;
-    for (size_t X = (size_t)blockIdx.x * blockDim.x + threadIdx.x; X < h; X += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)X, log_h)));
-        ef::E4 d;
-        d.c[0] = bb::sub(x, z.c[0]);
-        d.c[1] = bb::neg(z.c[1]);
-        d.c[2] = bb::neg(z.c[2]);
-        d.c[3] = bb::neg(z.c[3]);
-        const ef::E4 r = ef_inv(d);
-        out[X] = make_uint4(r.c[0], r.c[1], r.c[2], r.c[3]);
+    const uint32_t W = bb::MONTY_W;
+    const uint32_t a1 = neg(z.c[1]), a2 = neg(z.c[2]), a3 = neg(z.c[3]);
+    const uint32_t a1a3 = mmul(a1, a3);
+    const uint32_t C0 = sub(mmul(W, mmul(a2, a2)), mmul(W, add(a1a3, a1a3)));
+    const uint32_t C1 = add(a2, a2), C2 = add(mmul(a1, a1), mmul(W, mmul(a3, a3)));
+    const uint32_t Wa2 = mmul(W, a2), Wa3 = mmul(W, a3);
+    auto finish = [&](uint32_t a0, uint32_t n0, uint32_t n1, uint32_t d) {
+        const uint32_t m0 = mmul(n0, d), m1 = neg(mmul(n1, d));
+        return make_uint4(add(mmul(a0, m0), mmul(Wa2, m1)), neg(add(mmul(a1, m0), mmul(Wa3, m1))),
+                          add(mmul(a0, m1), mmul(a2, m0)), neg(add(mmul(a1, m1), mmul(a3, m0))));
+    };
+    if (log_h < 3) {
+        for (size_t X = (size_t)blockIdx.x * blockDim.x + threadIdx.x; X < h; X += (size_t)gridDim.x * blockDim.x) {
+            const uint32_t a0 = sub(mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)X, log_h))), z.c[0]);
+            const uint32_t n0 = add(mmul(a0, a0), C0), n1 = sub(mmul(a0, C1), C2);
+            out[X] = finish(a0, n0, n1, bb_inv(sub(mmul(n0, n0), mmul(W, mmul(n1, n1)))));
+        }
+        return;
+    }
+    // w^bitrev3(j), j = 0..7
+    uint32_t cw[8];
+    cw[0] = bb::MONTY_ONE, cw[1] = rp.v[2], cw[2] = rp.v[1], cw[3] = mmul(rp.v[2], rp.v[1]), cw[4] = rp.v[0];
+    cw[5] = mmul(cw[1], cw[4]), cw[6] = mmul(cw[2], cw[4]), cw[7] = mmul(cw[3], cw[4]);
+    RootPows rp8;  // (w^8)^(2^k)
+    TS_UNROLL
+    for (int k = 0; k < 25; k++) rp8.v[k] = rp.v[k + 3];
+    rp8.v[25] = rp8.v[26] = rp8.v[27] = bb::MONTY_ONE;
+    const size_t per = h >> 3;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < per; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t base = mmul(g_monty, pow_from_table(rp8, brev_bits((uint32_t)t, log_h - 3)));
+        uint32_t a0[8], n0[8], n1[8], nrm[8], pre[8];
+        uint32_t run = bb::MONTY_ONE;
+        TS_UNROLL
+        for (int j = 0; j < 8; j++) {
+            a0[j] = sub(mmul(base, cw[j]), z.c[0]);
+            n0[j] = add(mmul(a0[j], a0[j]), C0);
+            n1[j] = sub(mmul(a0[j], C1), C2);
+            nrm[j] = sub(mmul(n0[j], n0[j]), mmul(W, mmul(n1[j], n1[j])));
+            pre[j] = run;                              // product of the nonzero norms before j
+            run = nrm[j] ? mmul(run, nrm[j]) : run;    // a zero norm (z on the domain) yields 0 like a^(p-2), without poisoning the batch
+        }
+        uint32_t inv = bb_inv(run);
+        TS_UNROLL
+        for (int j = 7; j >= 0; j--) {
+            const uint32_t d = nrm[j] ? mmul(inv, pre[j]) : 0u;
+            inv = nrm[j] ? mmul(inv, nrm[j]) : inv;
+            out[(size_t)j * per + t] = finish(a0[j], n0[j], n1[j], d);
+        }
     }
 }
 
@@ -76,6 +123,11 @@ __global__ void __launch_bounds__(256) inv_denoms_kernel(uint4 *out, int log_h, 
 // its sums in registers, so the number of partials is the grid size (a few per SM), not n / 128: the second kernel used to
 // add 16384 partials per column in ONE serial loop per thread, which was most of the time of Pcs::open at the C4 shape.
 constexpr int BARY_RB = 128;
+// t < 2 p 2^32  ->  congruent mod p 2^32 and below it (2 p^2 + p 2^32 < 2 p 2^32 < 2^64: two products fit on top of a folded sum)
+TS_D uint64_t fold64(uint64_t t) {
+    const uint32_t hi = (uint32_t)(t >> 32);
+    return ((uint64_t)bb::umin32(hi, hi - bb::P) << 32) | (uint32_t)t;
+}
 __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__restrict__ m, size_t n, uint32_t width, int log_h,
                                                           uint32_t g_monty, RootPows rp, const uint4 *__restrict__ inv_denoms,
                                                           uint4 *__restrict__ partial, int tpr_log) {
@@ -86,7 +138,7 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__res
     const size_t n_blocks = (n + BARY_RB - 1) / BARY_RB;
     for (uint32_t c0 = 0; c0 < width; c0 += tpr) {
         const uint32_t c = c0 + cl;
-        uint32_t acc[4] = {0, 0, 0, 0};
+        uint64_t acc[4] = {0, 0, 0, 0};  // running sums of products, kept below p 2^32 (fold64) and reduced once at the end
         for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
             const size_t r0 = blk * BARY_RB;
             __syncthreads();
@@ -101,23 +153,122 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__res
             }
             __syncthreads();
             if (c < width)
-                for (uint32_t i = 2 * lane; i < (uint32_t)BARY_RB; i += 2 * lanes) {
-                    const uint32_t v0 = r0 + i < n ? m[(r0 + i) * width + c] : 0u;
-                    const uint32_t v1 = r0 + i + 1 < n ? m[(r0 + i + 1) * width + c] : 0u;
+                for (uint32_t i0 = 2 * lane; i0 < (uint32_t)BARY_RB; i0 += 8 * lanes) {
+                    // four row pairs per step: the eight loads are issued before the first product (the kernel is bound by
+                    // loads in flight, not by arithmetic)
+                    uint32_t v[8];
                     TS_UNROLL
-                    for (int k = 0; k < 4; k++)
-                        acc[k] = bb::add(acc[k], bb::redc((uint64_t)v0 * ks[4 * i + k] + (uint64_t)v1 * ks[4 * i + 4 + k]));
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t i = i0 + 2 * lanes * q;
+                        const bool in = i < (uint32_t)BARY_RB;
+                        v[2 * q] = in && r0 + i < n ? m[(r0 + i) * width + c] : 0u;
+                        v[2 * q + 1] = in && r0 + i + 1 < n ? m[(r0 + i + 1) * width + c] : 0u;
+                    }
+                    TS_UNROLL
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t i = i0 + 2 * lanes * q;
+                        if (i < (uint32_t)BARY_RB) {
+                            TS_UNROLL
+                            for (int k = 0; k < 4; k++)
+                                acc[k] = fold64(acc[k] + (uint64_t)v[2 * q] * ks[4 * i + k] + (uint64_t)v[2 * q + 1] * ks[4 * i + 4 + k]);
+                        }
+                    }
                 }
         }
+        uint32_t a[4];
         TS_UNROLL
-        for (int k = 0; k < 4; k++) red[4 * threadIdx.x + k] = acc[k];
+        for (int k = 0; k < 4; k++) red[4 * threadIdx.x + k] = a[k] = bb::redc(acc[k]);
         __syncthreads();
         if (lane == 0 && c < width) {
             for (uint32_t l = 1; l < lanes; l++) {
                 TS_UNROLL
-                for (int k = 0; k < 4; k++) acc[k] = bb::add(acc[k], red[4 * ((l << tpr_log) + cl) + k]);
+                for (int k = 0; k < 4; k++) a[k] = bb::add(a[k], red[4 * ((l << tpr_log) + cl) + k]);
             }
-            partial[(size_t)blockIdx.x * width + c] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            partial[(size_t)blockIdx.x * width + c] = make_uint4(a[0], a[1], a[2], a[3]);
+        }
+    }
+}
+// The same sums for widths that are multiples of 4 (every committed trace): a thread owns FOUR columns and reads them with one
+// 16-byte load per row, eight rows per batch.  The scalar kernel above is bound by bytes in flight (4 B x 8 loads per thread:
+// 1.2 TB/s on the 2^21 x 200 low coset, measured); this one keeps 128 B per thread in flight.
+// Threads = (256 >> tq_log) row lanes x (1 << tq_log) column quads; 16 running 64-bit sums per thread.
+constexpr int BARY4_RB = 256;
+__global__ void __launch_bounds__(256, 2) bary_partial4_kernel(const uint4 *__restrict__ m, size_t n, uint32_t quads, int log_h,
+                                                               uint32_t g_monty, RootPows rp, const uint4 *__restrict__ inv_denoms,
+                                                               uint4 *__restrict__ partial, int tq_log) {
+    TS_DYN_SMEM(uint32_t, sm);  // BARY4_RB x 4 weights, then 256 x 16 words for the lane reduction
+    uint4 *ks = reinterpret_cast<uint4 *>(sm);
+    uint32_t *red = sm + BARY4_RB * 4;
+    const uint32_t tq = 1u << tq_log, lanes = 256u >> tq_log;
+    const uint32_t lane = threadIdx.x >> tq_log, cq = threadIdx.x & (tq - 1);
+    const size_t n_blocks = (n + BARY4_RB - 1) / BARY4_RB;
+    for (uint32_t q0 = 0; q0 < quads; q0 += tq) {
+        const uint32_t q = q0 + cq;
+        uint64_t acc[4][4];
+        TS_UNROLL
+        for (int j = 0; j < 4; j++) {
+            TS_UNROLL
+            for (int k = 0; k < 4; k++) acc[j][k] = 0;
+        }
+        for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+            const size_t r0 = blk * BARY4_RB;
+            __syncthreads();
+            {
+                const uint32_t i = threadIdx.x;
+                uint4 k = make_uint4(0, 0, 0, 0);
+                if (r0 + i < n) {
+                    const uint32_t x = bb::mmul(g_monty, pow_from_table(rp, brev_bits((uint32_t)(r0 + i), log_h)));
+                    const uint4 d = inv_denoms[r0 + i];
+                    k = make_uint4(bb::mmul(x, d.x), bb::mmul(x, d.y), bb::mmul(x, d.z), bb::mmul(x, d.w));
+                }
+                ks[i] = k;
+            }
+            __syncthreads();
+            if (q < quads)
+                for (uint32_t i0 = lane; i0 < (uint32_t)BARY4_RB; i0 += 8 * lanes) {
+                    uint4 v[8];
+                    TS_UNROLL
+                    for (int s_ = 0; s_ < 8; s_++) {
+                        const uint32_t i = i0 + (uint32_t)s_ * lanes;
+                        v[s_] = (i < (uint32_t)BARY4_RB && r0 + i < n) ? m[(r0 + i) * quads + q] : make_uint4(0, 0, 0, 0);
+                    }
+                    TS_UNROLL
+                    for (int s_ = 0; s_ < 8; s_ += 2) {
+                        const uint32_t i = i0 + (uint32_t)s_ * lanes, i2 = i + lanes;
+                        if (i < (uint32_t)BARY4_RB) {
+                            const uint4 ka = ks[i], kb = i2 < (uint32_t)BARY4_RB ? ks[i2] : make_uint4(0, 0, 0, 0);
+                            const uint32_t va[4] = {v[s_].x, v[s_].y, v[s_].z, v[s_].w};
+                            const uint32_t vb[4] = {v[s_ + 1].x, v[s_ + 1].y, v[s_ + 1].z, v[s_ + 1].w};
+                            TS_UNROLL
+                            for (int j = 0; j < 4; j++) {
+                                acc[j][0] = fold64(acc[j][0] + (uint64_t)va[j] * ka.x + (uint64_t)vb[j] * kb.x);
+                                acc[j][1] = fold64(acc[j][1] + (uint64_t)va[j] * ka.y + (uint64_t)vb[j] * kb.y);
+                                acc[j][2] = fold64(acc[j][2] + (uint64_t)va[j] * ka.z + (uint64_t)vb[j] * kb.z);
+                                acc[j][3] = fold64(acc[j][3] + (uint64_t)va[j] * ka.w + (uint64_t)vb[j] * kb.w);
+                            }
+                        }
+                    }
+                }
+        }
+        uint32_t a[4][4];
+        __syncthreads();  // `red` of the previous column group has been read
+        TS_UNROLL
+        for (int j = 0; j < 4; j++) {
+            TS_UNROLL
+            for (int k = 0; k < 4; k++) red[16 * threadIdx.x + 4 * j + k] = a[j][k] = bb::redc(acc[j][k]);
+        }
+        __syncthreads();
+        if (lane == 0 && q < quads) {
+            for (uint32_t l = 1; l < lanes; l++) {
+                TS_UNROLL
+                for (int j = 0; j < 4; j++) {
+                    TS_UNROLL
+                    for (int k = 0; k < 4; k++) a[j][k] = bb::add(a[j][k], red[16 * ((l << tq_log) + cq) + 4 * j + k]);
+                }
+            }
+            TS_UNROLL
+            for (int j = 0; j < 4; j++)
+                partial[(size_t)blockIdx.x * (4 * quads) + 4 * q + j] = make_uint4(a[j][0], a[j][1], a[j][2], a[j][3]);
         }
     }
 }

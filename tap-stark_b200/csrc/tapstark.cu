@@ -1181,7 +1181,7 @@ int hash_rows(ts_ctx *c, const std::vector<const ts_matrix *> &mats, const std::
 // launches the small FRI rounds cost.  TS_TREE3_MIN_LOG overrides (A/B in profiles/r02/README.md).
 int tree3_min_log() {
     if (const char *e = getenv("TS_TREE3_MIN_LOG")) return std::max(3, atoi(e));
-    return 14;
+    return 19;  // measured on a B200: FRI commit phase of 2^24 elements 2.22 ms (14) / 2.12 (17) / 2.11 (19)
 }
 
 int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
@@ -1261,10 +1261,15 @@ int build_tree(ts_ctx *c, ts_tree *t, bool leaves_done = false) {
 
 // fill_leaves (optional): called with the leaf-digest array once it is allocated; it produces the matrix AND its row
 // hashes (the host pipeline), after which only the levels above the leaves are built here.
+// prealloc_digests (optional, single-matrix trees): a pool buffer of (2 hmax - 1) x 8 words whose leaf layer is already filled
+// (fold_hash_kernel); the tree takes it over -- also when the call fails.
 int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, int take_ownership,
                 uint8_t root[32], ts_tree **out, bool sync_root,
-                const std::function<int(uint32_t *)> *fill_leaves = nullptr) {
-    if (n_mats == 0) TS_FAIL(ctx, TS_ERR_ARG, "mmcs: no matrices");
+                const std::function<int(uint32_t *)> *fill_leaves = nullptr, uint32_t *prealloc_digests = nullptr) {
+    if (n_mats == 0) {
+        if (prealloc_digests) pool_release(ctx, prealloc_digests);
+        TS_FAIL(ctx, TS_ERR_ARG, "mmcs: no matrices");
+    }
     ts_tree *t = new ts_tree;
     t->ctx = ctx;
     t->mats.assign(mats, mats + n_mats);
@@ -1280,6 +1285,7 @@ int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, 
         if (log2_strict(mats[i]->rows) < 0) {
             t->own_mats = false;
             ts_tree_free(t);
+            if (prealloc_digests) pool_release(ctx, prealloc_digests);
             TS_FAIL(ctx, TS_ERR_ARG, "mmcs: heights must be powers of two");
         }
     t->lmax = (unsigned)log2_strict(t->hmax);
@@ -1288,14 +1294,16 @@ int mmcs_commit(ts_ctx *ctx, ts_matrix *const *mats, size_t n_mats, int layout, 
         t->layer_off.push_back(off);
         off += t->hmax >> l;
     }
-    cudaError_t e = pool_alloc(ctx, (void **)&t->digests, off * 32);
+    cudaError_t e = cudaSuccess;
+    if (prealloc_digests) t->digests = prealloc_digests;
+    else e = pool_alloc(ctx, (void **)&t->digests, off * 32);
     if (e != cudaSuccess) {
         t->own_mats = false;
         ts_tree_free(t);
         TS_FAIL(ctx, TS_ERR_CUDA, std::string("cudaMalloc digests: ") + cudaGetErrorString(e));
     }
     int rc = fill_leaves ? (*fill_leaves)(t->digests) : TS_OK;
-    if (rc == TS_OK) rc = build_tree(ctx, t, fill_leaves != nullptr);
+    if (rc == TS_OK) rc = build_tree(ctx, t, fill_leaves != nullptr || prealloc_digests != nullptr);
     if (rc == TS_OK && root) {
         cudaError_t e2 = cudaMemcpyAsync(root, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToHost,
                                          ctx->stream);
@@ -1358,6 +1366,45 @@ int fold_ext_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t
     TS_LAUNCH(kfn, blocks, fold::FOLD_T, 0, c->stream, (const uint4 *)in, (uint4 *)out, (const uint4 *)addend, log_h,
               first, h, hb, rp, dl, (const uint32_t *)c->fold_tlo, beta_canon ? (const uint32_t *)nullptr : half_beta_dev);
     return check_launch(c, "fold_ext_kernel");
+}
+
+// fold + the leaf hashes of the next round's tree (fold.cuh: fold_hash_kernel); log_h >= 9.  next_digests: (h/2) x 8 words.
+bool fold_hash_eligible(int log_h) { return log_h >= 9 && getenv("TS_NO_FOLD_HASH") == nullptr; }
+int fold_hash_launch(ts_ctx *c, const uint32_t *in, uint32_t *out, const uint32_t *addend, int log_h, const uint32_t beta_canon[4],
+                     const uint32_t *half_beta_dev, uint32_t *next_digests, size_t first = 0, size_t h_local = 0) {
+    const uint32_t half = bb::cinv(2);
+    ef::E4 hb;
+    for (int i = 0; i < 4; i++) hb.c[i] = beta_canon ? h_to_monty(bb::cmul(beta_canon[i], half)) : 0;
+    if (!beta_canon && !half_beta_dev) TS_FAIL(c, TS_ERR_ARG, "fold: no beta");
+    const uint32_t g_inv = bb::cinv(bb::two_adic_generator(log_h + 1));
+    fold::InvRootPows rp;
+    uint32_t r = g_inv;
+    for (int k = 0; k < 28; k++) {
+        rp.v[k] = h_to_monty(r);
+        r = bb::cmul(r, r);
+    }
+    fold::ChunkDeltas dl;
+    const int Lh = log_h - 9;  // chunk = 512 outputs = 256 leaves of the next tree
+    for (int t = 0; t < 28; t++) {
+        uint32_t v = 1;
+        if (Lh > 0 && t < Lh) {
+            int64_t delta = (int64_t)1 << (Lh - 1 - t);
+            for (int k = 0; k < t; k++) delta -= (int64_t)1 << (Lh - 1 - k);
+            const int64_t order = (int64_t)2 << log_h;
+            delta = ((delta % order) + order) % order;
+            v = bb::cpow(g_inv, (uint64_t)delta);
+        }
+        dl.v[t] = h_to_monty(v);
+    }
+    const size_t h = h_local ? h_local : (size_t)1 << log_h;
+    if ((first | h) & 511) TS_FAIL(c, TS_ERR_ARG, "fold_hash: range must be a multiple of 512 rows");
+    const size_t chunks = h >> 9;
+    KScope ks(c, TS_K_FOLD);
+    auto kfn = fold::fold_hash_kernel;
+    TS_LAUNCH(kfn, (unsigned)std::min<size_t>(chunks, (size_t)c->num_sms * 8), fold::FOLD_T, 0, c->stream, (const uint4 *)in,
+              (uint4 *)out, (const uint4 *)addend, log_h, first, h, hb, rp, dl, beta_canon ? (const uint32_t *)nullptr : half_beta_dev,
+              next_digests);
+    return check_launch(c, "fold_hash_kernel");
 }
 
 }  // namespace
@@ -2047,6 +2094,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
             TS_FAIL(c, TS_ERR_ARG, "commit phase: inputs must be sorted by strictly descending length");
     }
     size_t len = inputs[0]->rows, next_in = 1, round = 0;
+    uint32_t *next_digests = nullptr;  // digest buffer of the next round's tree, leaf layer filled by fold_hash_kernel
     // current layer.  When prover data is kept, round 0 commits to a clone of the first input
     // (`folded.clone()`, prover.rs:112) so every returned tree owns its layer; otherwise it is borrowed.
     uint32_t *cur = inputs[0]->d;
@@ -2130,7 +2178,9 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         ts_matrix *leaves = new ts_matrix{c, cur, h, 8, cur_owned};
         ts_tree *tree = nullptr;
         uint8_t root[32];
-        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, d_chain ? nullptr : root, &tree, true);  // prover.rs:113
+        uint32_t *filled = next_digests;  // leaf layer already hashed by the previous round's fold_hash_kernel
+        next_digests = nullptr;
+        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, d_chain ? nullptr : root, &tree, true, nullptr, filled);  // prover.rs:113
         if (rc != TS_OK) {
             ts_matrix_free(leaves);
             cur = nullptr;
@@ -2160,7 +2210,16 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         } else {
             const uint32_t *addend = nullptr;
             if (next_in < n_inputs && inputs[next_in]->rows == h) addend = inputs[next_in++]->d;  // prover.rs:124-126
-            rc = fold_ext_launch(c, cur, nf, addend, log2_strict(h), d_chain ? nullptr : beta, 0, 0, d_chain ? d_chain + 8 : nullptr);  // prover.rs:119
+            // the next iteration commits to nf as h/2 rows unless it is the last one or goes to the tail kernel
+            const bool next_is_tail = h <= ((size_t)1 << ftail::MAX_LOG_LEN) && next_in >= n_inputs && getenv("TS_NO_FRI_TAIL") == nullptr;
+            if (h > blowup && !next_is_tail && fold_hash_eligible(log2_strict(h)) &&
+                pool_alloc(c, (void **)&next_digests, (h - 1) * 32) == cudaSuccess) {
+                rc = fold_hash_launch(c, cur, nf, addend, log2_strict(h), d_chain ? nullptr : beta, d_chain ? d_chain + 8 : nullptr,
+                                      next_digests);  // prover.rs:119 + the row hashes of :112-113
+            } else {
+                next_digests = nullptr;
+                rc = fold_ext_launch(c, cur, nf, addend, log2_strict(h), d_chain ? nullptr : beta, 0, 0, d_chain ? d_chain + 8 : nullptr);  // prover.rs:119
+            }
         }
         cur = nullptr;
         cur_owned = false;
@@ -2195,6 +2254,7 @@ int ts_fri_commit_phase(ts_ctx *c, ts_matrix *const *inputs, size_t n_inputs, un
         }
     }
     if (d_chain) pool_release(c, d_chain);
+    if (next_digests) pool_release(c, next_digests);
     if (cur_owned && cur) pool_release(c, cur);
     if (rounds_out) *rounds_out = round;
     return rc;
@@ -2294,6 +2354,12 @@ int ts_pcs_get_evaluations_on_domain(ts_ctx *c, const ts_tree *t, size_t idx, si
 // roundup16(width) entries (columns past the width are multiplied by zero-filled data)
 static int dot_ext_powers_launch(ts_ctx *c, const ts_matrix *m, const uint32_t *apow_dev, ts_matrix *o, int accumulate) {
     KScope ks(c, TS_K_MISC);
+    if ((m->width == 4 || m->width == 8) && getenv("TS_NO_FAST") == nullptr) {
+        auto kfn = fold::dot_rows_small_kernel;
+        TS_LAUNCH(kfn, (unsigned)std::min<size_t>((m->rows + 255) / 256, (size_t)c->num_sms * 16), 256, 0, c->stream,
+                  (const uint4 *)m->d, m->rows, (uint32_t)(m->width / 4), (const uint4 *)apow_dev, (uint4 *)o->d, accumulate);
+        return check_launch(c, "dot_rows_small_kernel");
+    }
     if ((m->width & 3) == 0 && getenv("TS_NO_FAST") == nullptr) {
         auto kfn = fold::dot_rows_fast_kernel;
         const size_t per_block = (size_t)fold::DOT_FAST_WARPS * 32;
@@ -2527,11 +2593,13 @@ int ts_interpolate_low_coset(ts_ctx *c, const ts_matrix *lde, size_t n, const ui
     const int log_n = log2_strict(n), log_h = log2_strict(lde->rows);
     if (log_n < 0 || log_h < 0 || n > lde->rows || inv_denoms->rows < n || inv_denoms->width != 4)
         TS_FAIL(c, TS_ERR_ARG, "interpolate_low_coset: bad sizes");
-    const size_t w = lde->width, n_blocks = (n + opn::BARY_RB - 1) / opn::BARY_RB;
-    size_t n_ctas = std::min<size_t>(n_blocks, (size_t)c->num_sms * 4);
+    const size_t w = lde->width;
+    const bool quad = (w & 3) == 0 && getenv("TS_NO_BARY4") == nullptr;  // 16-byte row loads (every committed trace)
+    const size_t n_blocks = quad ? (n + opn::BARY4_RB - 1) / opn::BARY4_RB : (n + opn::BARY_RB - 1) / opn::BARY_RB;
+    size_t n_ctas = std::min<size_t>(n_blocks, (size_t)c->num_sms * (quad ? 2 : 4));
     if (const char *e = getenv("TS_BARY_CTAS")) n_ctas = std::max<size_t>(1, std::min<size_t>(n_blocks, strtoul(e, nullptr, 10)));  // test hook
-    int tpr_log = 0;  // threads per row: the smallest power of two >= width, at most 256
-    while (tpr_log < 8 && ((size_t)1 << tpr_log) < w) tpr_log++;
+    int tpr_log = 0;  // threads per row: the smallest power of two >= width (column quads when `quad`), at most 256
+    while (tpr_log < 8 && ((size_t)1 << tpr_log) < (quad ? w / 4 : w)) tpr_log++;
     uint4 *partial = nullptr, *ys = nullptr;
     TS_CUDA(c, pool_alloc(c, (void **)&partial, n_ctas * w * 16));
     cudaError_t e = pool_alloc(c, (void **)&ys, w * 16);
@@ -2543,10 +2611,17 @@ int ts_interpolate_low_coset(ts_ctx *c, const ts_matrix *lde, size_t n, const ui
     {
         // the low coset of the committed LDE: rows r < n hold p(g * w_n^bitrev_n(r))
         KScope ks(c, TS_K_MISC);
-        auto kfn = opn::bary_partial_kernel;
-        TS_LAUNCH(kfn, (unsigned)n_ctas, 256, (size_t)(opn::BARY_RB + 256) * 16, c->stream, (const uint32_t *)lde->d, n, (uint32_t)w,
-                  log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial, tpr_log);
-        rc = check_launch(c, "bary_partial_kernel");
+        if (quad) {
+            auto kfn = opn::bary_partial4_kernel;
+            TS_LAUNCH(kfn, (unsigned)n_ctas, 256, (size_t)(opn::BARY4_RB * 4 + 256 * 16) * 4, c->stream, (const uint4 *)lde->d, n,
+                      (uint32_t)(w / 4), log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial, tpr_log);
+            rc = check_launch(c, "bary_partial4_kernel");
+        } else {
+            auto kfn = opn::bary_partial_kernel;
+            TS_LAUNCH(kfn, (unsigned)n_ctas, 256, (size_t)(opn::BARY_RB + 256) * 16, c->stream, (const uint32_t *)lde->d, n, (uint32_t)w,
+                      log_n, h_to_monty(31), root_pows(log_n), (const uint4 *)inv_denoms->d, partial, tpr_log);
+            rc = check_launch(c, "bary_partial_kernel");
+        }
     }
     if (rc == TS_OK) {
         KScope ks(c, TS_K_MISC);
@@ -2856,11 +2931,14 @@ int ts_fri_commit_phase_sharded(ts_ctx *c, const uint32_t *cur_dev, size_t len_g
     bool cur_owned = false;
     size_t len_g = len_global, local = len_global / world;
     int rc = TS_OK;
+    uint32_t *next_digests = nullptr;
     for (size_t r = 0; r < n_rounds && rc == TS_OK; r++) {
         const size_t h_g = len_g / 2, h_l = local / 2;
         ts_matrix *leaves = new ts_matrix{c, cur, h_l, 8, cur_owned};
         ts_tree *tree = nullptr;
-        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, nullptr, &tree, false);
+        uint32_t *filled = next_digests;  // sub-tree leaf layer already hashed by the previous round's fold_hash_kernel
+        next_digests = nullptr;
+        rc = mmcs_commit(c, &leaves, 1, TS_LAYOUT_P3_INJECT, 1, nullptr, &tree, false, nullptr, filled);
         if (rc != TS_OK) {
             ts_matrix_free(leaves);
             cur = nullptr;
@@ -2884,13 +2962,22 @@ int ts_fri_commit_phase_sharded(ts_ctx *c, const uint32_t *cur_dev, size_t len_g
             c->err = "fri sharded: layer allocation failed";
             rc = TS_ERR_CUDA;
         }
-        if (rc == TS_OK) rc = fold_ext_launch(c, cur, nf, nullptr, log2_strict(h_g), nullptr, rank * h_l, h_l, chain + 8);
+        if (rc == TS_OK) {
+            if (r + 1 < n_rounds && (h_l & 511) == 0 && fold_hash_eligible(log2_strict(h_g)) &&
+                pool_alloc(c, (void **)&next_digests, (h_l - 1) * 32) == cudaSuccess) {
+                rc = fold_hash_launch(c, cur, nf, nullptr, log2_strict(h_g), nullptr, chain + 8, next_digests, rank * h_l, h_l);
+            } else {
+                next_digests = nullptr;
+                rc = fold_ext_launch(c, cur, nf, nullptr, log2_strict(h_g), nullptr, rank * h_l, h_l, chain + 8);
+            }
+        }
         ts_tree_free(tree);  // releases the layer it owns (stream-ordered pool)
         cur = nf;
         cur_owned = r + 1 < n_rounds;
         len_g = h_g;
         local = h_l;
     }
+    if (next_digests) pool_release(c, next_digests);
     if (rc != TS_OK) {
         if (cur_owned && cur) pool_release(c, cur);
         ts_fri_chain_end(c, chain, nullptr, 0, nullptr);
@@ -2907,6 +2994,15 @@ int ts_fri_fold_ext_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, si
     uint32_t beta[4];
     for (int i = 0; i < 4; i++) beta[i] = h_from_monty(beta_monty[i]);
     return fold_ext_launch(c, in_dev, out_dev, addend_dev, lh, beta, first, h_local);
+}
+
+int ts_fri_fold_hash_shard(ts_ctx *c, const uint32_t *in_dev, size_t h_global, size_t first, size_t h_local,
+                           const uint32_t beta_monty[4], const uint32_t *addend_dev, uint32_t *out_dev, uint32_t *next_digests_dev) {
+    const int lh = log2_strict(h_global);
+    if (lh < 9 || lh > 26 || first + h_local > h_global || !next_digests_dev) TS_FAIL(c, TS_ERR_ARG, "fold_hash shard: bad range");
+    uint32_t beta[4];
+    for (int i = 0; i < 4; i++) beta[i] = h_from_monty(beta_monty[i]);
+    return fold_hash_launch(c, in_dev, out_dev, addend_dev, lh, beta, nullptr, next_digests_dev, first, h_local);
 }
 
 // ---------------------------------------------------------------- Pcs::open + bf_prove behind the ABI, proof bytes

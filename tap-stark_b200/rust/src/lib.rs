@@ -135,7 +135,7 @@ impl GpuContext {
         }
     }
     /// Page-locks a long-lived host buffer (a trace `Vec<BabyBear>`) so the `*_host` entry points copy it at the
-    /// PCIe rate; pageable sources work too, at the driver's staging rate (bench.py reports both).
+    /// PCIe rate; pageable sources work too, staged through the library's bounce buffers (bench.py reports both).
     pub fn pin<T>(&self, v: &[T]) {
         let rc = unsafe { sys::ts_host_register(self.0, v.as_ptr() as *const c_void, core::mem::size_of_val(v)) };
         self.check(rc, "ts_host_register");

@@ -76,6 +76,41 @@ def check_fold_ext(ts, ctx, orc, log_h, seed=4):
     assert np.array_equal(got, orc.fold_matrix_ef(vals, beta)), f"fold mismatch log_h={log_h}"
 
 
+def check_fold_hash_shard(ts, ctx, orc, log_h, shards, with_addend, seed=44):
+    """ts_fri_fold_hash_shard: every shard's folded rows equal the oracle's fold (+ the next input), and the digests it emits are
+    Blake3 of the next round's rows (two folded extension elements as canonical LE words, fri/src/prover.rs:112-113)."""
+    import ctypes as C
+
+    h = 1 << log_h
+    vals = rand_mat(seed, 2 * h, 4)
+    beta = rand_mat(seed + 1, 1, 4)[0]
+    addend = rand_mat(seed + 2, h, 4) if with_addend else None
+    want = orc.fold_matrix_ef(vals, beta)
+    if with_addend:
+        want = ((want.astype(np.uint64) + addend) % P).astype(np.uint32)
+    L = ts.lib()
+    src = ts.DeviceMatrix.from_canonical(ctx, vals.reshape(h, 8))
+    add_d = ts.DeviceMatrix.from_canonical(ctx, addend) if with_addend else None
+    bm = ts.to_monty(beta)
+    h_l = h // shards
+    for r in range(shards):
+        out = ts.DeviceMatrix.from_canonical(ctx, np.zeros((h_l, 4), dtype=np.uint32))
+        dig = ts.DeviceMatrix.from_canonical(ctx, np.zeros((h_l // 2, 8), dtype=np.uint32))
+        ctx.check(L.ts_fri_fold_hash_shard(ctx._h, C.c_void_p(src.device_ptr + r * h_l * 32), h, r * h_l, h_l,
+                                           bm.ctypes.data_as(C.c_void_p),
+                                           C.c_void_p(add_d.device_ptr + r * h_l * 16) if with_addend else None,
+                                           C.c_void_p(out.device_ptr), C.c_void_p(dig.device_ptr)), "fold_hash_shard")
+        got = out.to_canonical()
+        assert np.array_equal(got, want[r * h_l : (r + 1) * h_l]), f"fold_hash shard {r}/{shards} log_h={log_h}"
+        d = dig.to_monty_host()  # raw digest words
+        rows = want[r * h_l : (r + 1) * h_l].reshape(-1, 8)
+        for j in sorted({0, 1, h_l // 4, h_l // 2 - 1}):
+            assert d[j].astype("<u4").tobytes() == orc.blake3(rows[j].astype("<u4").tobytes()), f"digest {j} of shard {r}"
+    if log_h >= 9:
+        assert L.ts_fri_fold_hash_shard(ctx._h, C.c_void_p(src.device_ptr), h, 256, 256, bm.ctypes.data_as(C.c_void_p), None,
+                                        C.c_void_p(src.device_ptr), C.c_void_p(src.device_ptr)) != 0  # not a multiple of 512
+
+
 def check_fold_base_reference_property(ts, ctx, orc, log_n=10, seed=5):
     """fri/src/fold_even_odd.rs:65-95 verbatim, on the device path."""
     n = 1 << log_n

@@ -171,7 +171,8 @@ def test_mmcs_incremental_commit(ts, ctx, orc, rows, bw, nb, windows):
     ctx._L.ts_tree_free(th)
 
 
-@pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {}])
+@pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {},
+                                 {"TS_NO_FRI_TAIL": "1", "TS_NO_FOLD_HASH": "1"}])
 def test_commit_phase_round_forms(ts, ctx, orc, monkeypatch, env):
     """The three forms of a commit-phase round produce one transcript: chained on the device (sponge_step_kernel, beta read
     by the fold kernel from device memory), the single-CTA tail, and the round-1 form with a host sponge per round."""
@@ -179,6 +180,12 @@ def test_commit_phase_round_forms(ts, ctx, orc, monkeypatch, env):
         monkeypatch.setenv(k, v)
     pc.check_commit_phase(ts, ctx, orc, [12], 2, seed=31)
     pc.check_commit_phase(ts, ctx, orc, [8, 6, 3], 1, seed=32)
+    pc.check_commit_phase(ts, ctx, orc, [11, 10, 9], 1, seed=33)  # later inputs added inside fold_hash_kernel (prover.rs:124-126)
+
+
+@pytest.mark.parametrize("log_h,shards,with_addend", [(9, 1, False), (10, 2, True), (12, 4, False)])
+def test_fold_hash_shard(ts, ctx, orc, log_h, shards, with_addend):
+    pc.check_fold_hash_shard(ts, ctx, orc, log_h, shards, with_addend)
 
 
 def test_commit_phase_golden(ts, ctx, orc, golden):
@@ -201,11 +208,13 @@ def test_pcs_commit(ts, ctx, orc):
 def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
+    pc.check_dot_ext_powers(ts, ctx, orc, 1000, 4)   # one thread per row (quotient chunks)
+    pc.check_dot_ext_powers(ts, ctx, orc, 77, 8)
     pc.check_dot_ext_powers(ts, ctx, orc, 300, 72)   # width % 4 == 0: fast kernel, partial last block
     pc.check_dot_ext_powers(ts, ctx, orc, 33, 256)
 
 
-@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1)])
+@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1), (7, 1100, 1), (7, 301, 2), (11, 8, 3)])
 def test_interpolate_low_coset(ts, ctx, orc, monkeypatch, log_n, width, ctas):
     """Row-lane mapping for narrow matrices, one lane for wide ones, column groups past 256, grid-stride row blocks."""
     if ctas is not None:
@@ -307,9 +316,10 @@ def test_stark_quotient_golden(ts, ctx, golden):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-def test_mmcs_big_layers(ts, ctx, orc, layout):
-    """Layers of >= 2^14 children go through tree_reduce3_kernel (one thread per 8 children, three levels per launch),
-    here followed by an injection layer (2^12 rows) and the shared-memory kernel for the top."""
+def test_mmcs_big_layers(ts, ctx, orc, monkeypatch, layout):
+    """Big layers go through tree_reduce3_kernel (one thread per 8 children, three levels per launch; from 2^19 children by
+    default, from 2^14 here), followed by an injection layer (2^12 rows) and the shared-memory kernel for the top."""
+    monkeypatch.setenv("TS_TREE3_MIN_LOG", "14")
     pc.check_mmcs(ts, ctx, orc, [(1 << 16, 3), (1 << 12, 5)], layout, indices=(0, 4097, (1 << 16) - 1))
 
 

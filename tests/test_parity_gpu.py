@@ -197,7 +197,8 @@ def test_mmcs_incremental_commit(ts, ctx, orc, rows, bw, nb, windows):
     ctx._L.ts_tree_free(th)
 
 
-@pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {}])
+@pytest.mark.parametrize("env", [{"TS_NO_FRI_TAIL": "1"}, {"TS_NO_FRI_CHAIN": "1"}, {"TS_NO_FRI_CHAIN": "1", "TS_NO_FRI_TAIL": "1"}, {},
+                                 {"TS_NO_FRI_TAIL": "1", "TS_NO_FOLD_HASH": "1"}, {"TS_TREE3_MIN_LOG": "14"}])
 def test_commit_phase_round_forms(ts, ctx, orc, monkeypatch, env):
     """The three forms of a commit-phase round produce one transcript: chained on the device (sponge_step_kernel, beta read
     by the fold kernel from device memory), the single-CTA tail, and the round-1 form with a host sponge per round."""
@@ -205,6 +206,13 @@ def test_commit_phase_round_forms(ts, ctx, orc, monkeypatch, env):
         monkeypatch.setenv(k, v)
     pc.check_commit_phase(ts, ctx, orc, [12], 2, seed=31)
     pc.check_commit_phase(ts, ctx, orc, [8, 6, 3], 1, seed=32)
+    pc.check_commit_phase(ts, ctx, orc, [11, 10, 9], 1, seed=33)  # later inputs added inside fold_hash_kernel (prover.rs:124-126)
+    pc.check_commit_phase(ts, ctx, orc, [16], 2, seed=34)         # fused fold + leaf hash above the tail, all tree kernels
+
+
+@pytest.mark.parametrize("log_h,shards,with_addend", [(9, 1, False), (10, 2, True), (12, 4, False), (20, 8, True), (22, 2, False)])
+def test_fold_hash_shard(ts, ctx, orc, log_h, shards, with_addend):
+    pc.check_fold_hash_shard(ts, ctx, orc, log_h, shards, with_addend)
 
 
 def test_commit_phase_golden(ts, ctx, orc, golden):
@@ -258,6 +266,8 @@ def test_pcs_commit_host_pipelined(ts, ctx, orc, width):
 def test_dot_ext_powers(ts, ctx, orc):
     pc.check_dot_ext_powers(ts, ctx, orc, 100, 70)
     pc.check_dot_ext_powers(ts, ctx, orc, 64, 3)
+    pc.check_dot_ext_powers(ts, ctx, orc, 1000, 4)   # one thread per row (quotient chunks)
+    pc.check_dot_ext_powers(ts, ctx, orc, 77, 8)
     pc.check_dot_ext_powers(ts, ctx, orc, 1 << 12, 256)
 
 
@@ -435,7 +445,7 @@ def test_config5_fri_sweep(ts, ctx, orc, log_len, log_blowup):
     _replay_query_path(ts, orc, cfg, res, log_len, 987654321 % (1 << log_len))
 
 
-@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1),
+@pytest.mark.parametrize("log_n,width,ctas", [(3, 1, None), (9, 2, None), (10, 4, 3), (9, 60, 2), (9, 200, 3), (8, 300, 1), (7, 1100, 1), (7, 301, 2), (11, 8, 3),
                                               (18, 4, None), (17, 200, None)])
 def test_interpolate_low_coset(ts, ctx, orc, monkeypatch, log_n, width, ctas):
     """interpolate_coset on the device against sum_k c_k z^k; the last two shapes have more row blocks than CTAs."""
