@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) bary_partial_kernel(const uint32_t *__res
                         if (i < (uint32_t)BARY_RB) {
                             TS_UNROLL
                             for (int k = 0; k < 4; k++)
-                                acc[k] = fold64(acc[k] + (uint64_t)v[2 * q] * ks[4 * i + k] + (uint64_t)v[2 * q + 1] * ks[4 * i + 4 + k]);
+                                acc[k] = fold64(bb::madw(v[2 * q + 1], ks[4 * i + 4 + k], bb::madw(v[2 * q], ks[4 * i + k], acc[k])));
                         }
                     }
                 }
@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(256, 2) bary_partial4_kernel(const uint4 *__re
                             const uint32_t vb[4] = {v[s_ + 1].x, v[s_ + 1].y, v[s_ + 1].z, v[s_ + 1].w};
                             TS_UNROLL
                             for (int j = 0; j < 4; j++) {
-                                acc[j][0] = fold64(acc[j][0] + (uint64_t)va[j] * ka.x + (uint64_t)vb[j] * kb.x);
-                                acc[j][1] = fold64(acc[j][1] + (uint64_t)va[j] * ka.y + (uint64_t)vb[j] * kb.y);
-                                acc[j][2] = fold64(acc[j][2] + (uint64_t)va[j] * ka.z + (uint64_t)vb[j] * kb.z);
-                                acc[j][3] = fold64(acc[j][3] + (uint64_t)va[j] * ka.w + (uint64_t)vb[j] * kb.w);
+                                acc[j][0] = fold64(bb::madw(vb[j], kb.x, bb::madw(va[j], ka.x, acc[j][0])));
+                                acc[j][1] = fold64(bb::madw(vb[j], kb.y, bb::madw(va[j], ka.y, acc[j][1])));
+                                acc[j][2] = fold64(bb::madw(vb[j], kb.z, bb::madw(va[j], ka.z, acc[j][2])));
+                                acc[j][3] = fold64(bb::madw(vb[j], kb.w, bb::madw(va[j], ka.w, acc[j][3])));
                             }
                         }
                     }
