@@ -133,7 +133,6 @@ struct ts_tree {
     } while (0)
 
 namespace {
-
 struct KScope {  // counts a kernel launch and, when profiling, brackets it with events on the ctx stream
     ts_ctx *c;
     int kind;
@@ -189,8 +188,10 @@ cudaError_t pool_alloc(ts_ctx *c, void **p, size_t bytes) {
 #else
     const size_t sz = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
 #endif
-    auto it = c->pool_free.find(sz);
-    if (it != c->pool_free.end()) {
+    // best fit within 2x (and at most 64 MiB of slack): a prover with varying shapes reuses its cached blocks instead of holding
+    // one per distinct size; the block keeps its real size in pool_sizes
+    auto it = c->pool_free.lower_bound(sz);
+    if (it != c->pool_free.end() && (it->first == sz || (it->first <= 2 * sz && it->first - sz <= ((size_t)64 << 20)))) {
         *p = it->second;
         c->pool_free.erase(it);
         return cudaSuccess;
@@ -1827,20 +1828,18 @@ int ts_tree_root_copy(ts_ctx *c, const ts_tree *t, uint8_t *dst_device) {
     TS_CUDA(c, cudaMemcpyAsync(dst_device, t->digests + t->layer_off[t->lmax] * 8, 32, cudaMemcpyDeviceToDevice, c->stream));
     return TS_OK;
 }
+namespace {
+int open_many(ts_ctx *c, const ts_tree *t, const std::vector<size_t> &idx, std::vector<uint32_t> &rows, std::vector<uint8_t> &paths,
+              size_t *row_words_out);  // defined with ts_pcs_open below
+}
 int ts_mmcs_open_batch(ts_ctx *c, const ts_tree *t, size_t index, uint32_t *rows_out, uint8_t *path_out) {
-    if (index >= t->hmax) TS_FAIL(c, TS_ERR_ARG, "open_batch: index out of range");
-    size_t o = 0;
-    for (const ts_matrix *m : t->mats) {
-        const size_t row = index >> (t->lmax - (unsigned)log2_strict(m->rows));
-        TS_CUDA(c, cudaMemcpyAsync(rows_out + o, m->d + row * m->width, m->width * 4, cudaMemcpyDeviceToHost, c->stream));
-        o += m->width;
-    }
-    for (unsigned l = 0; l < t->lmax; l++) {
-        const size_t node = (index >> l) ^ 1;
-        TS_CUDA(c, cudaMemcpyAsync(path_out + 32 * l, t->digests + (t->layer_off[l] + node) * 8, 32,
-                                   cudaMemcpyDeviceToHost, c->stream));
-    }
-    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    // one gather launch and one read-back for the rows and the whole path (round 1: a 32-byte copy per tree level and per row)
+    std::vector<uint32_t> rows;
+    std::vector<uint8_t> path;
+    size_t row_words = 0;
+    TS_TRY(open_many(c, t, std::vector<size_t>{index}, rows, path, &row_words));
+    if (row_words) memcpy(rows_out, rows.data(), row_words * 4);
+    if (t->lmax) memcpy(path_out, path.data(), 32 * (size_t)t->lmax);
     return TS_OK;
 }
 int ts_tree_layer(ts_ctx *c, const ts_tree *t, size_t layer, uint8_t *out, size_t *n_nodes) {
