@@ -299,8 +299,9 @@ def run_b200(a):
         barrier()
         k = max(2, min(a.steps, 5))
         ev0.record(stream)
+        last_e = None
         for _ in range(k):
-            runner.step_e2e()
+            last_e = runner.step_e2e()
         ev1.record(stream)
         barrier()
         ms_e = ev0.elapsed_time(ev1) / k
@@ -309,7 +310,10 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e = float(t.item())
         e2e = {"value": elems / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes * world,
-               "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e}
+               "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": ms_e,
+               # the host-buffer call must produce the resident step's transcript (same trace)
+               "same_result_as_resident": bool(last and last_e and last_e["root"] == last["root"]
+                                               and list(last_e["final_poly"]) == list(last["final_poly"]))}
         runner.release_host()
         if world == 1 and hasattr(runner, "prepare_host"):
             # the same call on a PAGEABLE host trace (a Rust Vec that was not registered with ts_host_register): the library

@@ -278,17 +278,42 @@ class ShardedProver:
         recv, works, keep = [], [], []
         staged = []
         marks = [self._mark()]
+        slab = False
         if host_full is not None:
-            # strided column windows of the row-major pinned trace, transfer lane 0: window c+1 is copied while window c is
-            # transformed (ts_copy_join below makes the LDE of a window wait for exactly the copies issued before it)
+            # transfer lane 0: window c+1 is copied while window c is transformed (ts_copy_join below makes the LDE of a window
+            # wait for exactly the copies issued before it)
             W = host_full.shape[1]
+            # Two ways to read a rank's share out of the row-major pinned trace:
+            #   window: this rank's wc columns of ALL rows per chunk -- (wc * 4)-byte segments, 32 bytes at 8 GPUs, which PCIe
+            #           copies at a fraction of the link rate (measured: 49 ms per step from 4 GPUs on, whatever N)
+            #   slab  : ALL G * wc columns of the chunk for this rank's n / G ROWS -- 256-byte segments at every N -- followed by
+            #           an all-to-all over NVLink that hands every owner its columns (the transpose of the re-shard after the LDE)
+            slab = G > 1 and n % G == 0 and os.environ.get("TS_HOST_INPUT", "slab") == "slab"
+            nl_in, Wc = n // G, G * wc
             for c in range(C_):
-                staged.append(torch.empty((n, wc), dtype=torch.int32, device=self.device))
+                staged.append(torch.empty((nl_in, Wc) if slab else (n, wc), dtype=torch.int32, device=self.device))
 
             def issue_h2d(c):
+                if slab:
+                    src = host_full.data_ptr() + (r * nl_in * W + c * Wc) * 4
+                    ctx.check(L.ts_copy2d_async(ctx._h, 0, C.c_void_p(staged[c].data_ptr()), Wc * 4, C.c_void_p(src), W * 4, Wc * 4, nl_in,
+                                                1 if c == 0 else 0), "copy2d_async")
+                    return
                 src = host_full.data_ptr() + (c * G * wc + r * wc) * 4  # chunk-major ownership (owned_columns)
                 ctx.check(L.ts_copy2d_async(ctx._h, 0, C.c_void_p(staged[c].data_ptr()), wc * 4, C.c_void_p(src), W * 4, wc * 4, n,
                                             1 if c == 0 else 0), "copy2d_async")
+
+            def columns_to_owners(c):
+                """slab form: rows [r * n/G, ...) x the chunk's G * wc columns -> this rank's wc columns of all n rows"""
+                send = staged[c].view(nl_in, G, wc).permute(1, 0, 2).contiguous()  # [owner][row][column]
+                out = torch.empty((n, wc), dtype=torch.int32, device=self.device)  # rows in source-rank order = global row order
+                send_list, recv_list = list(send.unbind(0)), list(out.view(G, nl_in, wc).unbind(0))
+                if self.use_batched_p2p:
+                    self.exchange(send_list, recv_list)
+                else:
+                    dist.all_to_all(recv_list, send_list)
+                keep.append(send)
+                return out
 
             issue_h2d(0)
             ctx.check(L.ts_copy_join(ctx._h, 0), "copy_join")
@@ -349,9 +374,9 @@ class ShardedProver:
 
         for c in range(C_):
             if host_full is not None:
-                src_t = staged[c]
                 if c + 1 < C_:
                     issue_h2d(c + 1)
+                src_t = columns_to_owners(c) if slab else staged[c]
             elif host_panels is not None:
                 src_t, ev_ = staged[c]
                 torch.cuda.current_stream().wait_event(ev_)
