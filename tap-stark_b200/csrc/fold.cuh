@@ -237,10 +237,10 @@ __global__ void __launch_bounds__(256) dot_rows_small_kernel(const uint4 *__rest
                 TS_UNROLL
                 for (int i = 0; i < 4; i += 2) {
                     const uint4 a0 = a[4 * q + i], a1 = a[4 * q + i + 1];
-                    acc[0] = fold64(acc[0] + (uint64_t)w[i] * a0.x + (uint64_t)w[i + 1] * a1.x);
-                    acc[1] = fold64(acc[1] + (uint64_t)w[i] * a0.y + (uint64_t)w[i + 1] * a1.y);
-                    acc[2] = fold64(acc[2] + (uint64_t)w[i] * a0.z + (uint64_t)w[i + 1] * a1.z);
-                    acc[3] = fold64(acc[3] + (uint64_t)w[i] * a0.w + (uint64_t)w[i + 1] * a1.w);
+                    acc[0] = fold64(bb::madw(w[i + 1], a1.x, bb::madw(w[i], a0.x, acc[0])));
+                    acc[1] = fold64(bb::madw(w[i + 1], a1.y, bb::madw(w[i], a0.y, acc[1])));
+                    acc[2] = fold64(bb::madw(w[i + 1], a1.z, bb::madw(w[i], a0.z, acc[2])));
+                    acc[3] = fold64(bb::madw(w[i + 1], a1.w, bb::madw(w[i], a0.w, acc[3])));
                 }
             }
         }
