@@ -45,15 +45,48 @@ TS_D uint32_t fadd(uint32_t a, uint32_t b) {
 TS_D uint32_t fadd(uint32_t a, uint32_t b) { return a + b; }
 #endif
 
-#define TS_B3_G(a, b, c, d, mx, my) \
-    a = fadd(fadd(a, b), (mx));     \
-    d = rotr(d ^ a, 16);            \
-    c = fadd(c, d);                 \
-    b = rotr(b ^ c, 12);            \
-    a = fadd(fadd(a, b), (my));     \
-    d = rotr(d ^ a, 8);             \
-    c = fadd(c, d);                 \
+// A rotation on the fma pipe: x * 2^(32-n) as a 64-bit product holds the bits shifted out in its high word, and high + low is the
+// rotated word (no common bits).  Two fma instructions (IMAD.WIDE, IMAD) instead of one alu instruction (SHF): it pays only for
+// as many rotations as it takes to level the two pipes -- per G 8 alu + 6 fma instructions, a warp instruction occupying its
+// 16-lane pipe for two cycles, so moving ONE rotation in every second G gives alu 7.5 / fma 7 / issue 14.5 per G.
+// TS_B3_ROT_FMA = how many of the 8 G of a round do that with their rotation by 16.  Measured on the 2^24 x 1 KiB leaf hash
+// (profiles/r02/README.md): 0: 10.02 ms, 1: 9.96, **2: 9.61**, 3: 10.66, 4: 9.98 -- two, as the pipe arithmetic says.
+#ifndef TS_B3_ROT_FMA
+#define TS_B3_ROT_FMA 2
+#endif
+#if !defined(TS_EMULATE) && !defined(TS_B3_NO_FMA_ADDS)
+TS_D uint32_t rot16_fma(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi, r;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, 65536;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(c_one), "r"(lo));
+    return r;
+#else
+    return rotr(x, 16);
+#endif
+}
+#else
+TS_D uint32_t rot16_fma(uint32_t x) { return rotr(x, 16); }
+#endif
+
+#define TS_B3_G_(a, b, c, d, mx, my, ROT16) \
+    a = fadd(fadd(a, b), (mx));             \
+    d = ROT16(d ^ a);                       \
+    c = fadd(c, d);                         \
+    b = rotr(b ^ c, 12);                    \
+    a = fadd(fadd(a, b), (my));             \
+    d = rotr(d ^ a, 8);                     \
+    c = fadd(c, d);                         \
     b = rotr(b ^ c, 7);
+TS_D uint32_t rot16_alu(uint32_t x) { return rotr(x, 16); }
+#define TS_B3_G(a, b, c, d, mx, my) TS_B3_G_(a, b, c, d, mx, my, rot16_alu)
+// the g-th G of a round (g = 0..7): the first TS_B3_ROT_FMA of the sequence 0, 2, 4, 6, 1, 3, 5, 7 rotate on the fma pipe
+#define TS_B3_GSEL(g, a, b, c, d, mx, my)                                          \
+    if ((((g) & 1) ? 4 + ((g) >> 1) : ((g) >> 1)) < TS_B3_ROT_FMA) {                \
+        TS_B3_G_(a, b, c, d, mx, my, rot16_fma)                                     \
+    } else {                                                                        \
+        TS_B3_G_(a, b, c, d, mx, my, rot16_alu)                                     \
+    }
 
 // message schedule: word index used at (round, slot), i.e. the permutation applied r times
 struct Sched {
@@ -75,14 +108,14 @@ TS_D void compress(uint32_t (&cv)[8], const uint32_t (&m)[16], uint32_t counter,
     uint32_t s12 = counter, s13 = 0u, s14 = block_len, s15 = flags;
     TS_UNROLL
     for (int r = 0; r < 7; r++) {
-        TS_B3_G(s0, s4, s8, s12, m[S.s[r][0]], m[S.s[r][1]])
-        TS_B3_G(s1, s5, s9, s13, m[S.s[r][2]], m[S.s[r][3]])
-        TS_B3_G(s2, s6, s10, s14, m[S.s[r][4]], m[S.s[r][5]])
-        TS_B3_G(s3, s7, s11, s15, m[S.s[r][6]], m[S.s[r][7]])
-        TS_B3_G(s0, s5, s10, s15, m[S.s[r][8]], m[S.s[r][9]])
-        TS_B3_G(s1, s6, s11, s12, m[S.s[r][10]], m[S.s[r][11]])
-        TS_B3_G(s2, s7, s8, s13, m[S.s[r][12]], m[S.s[r][13]])
-        TS_B3_G(s3, s4, s9, s14, m[S.s[r][14]], m[S.s[r][15]])
+        TS_B3_GSEL(0, s0, s4, s8, s12, m[S.s[r][0]], m[S.s[r][1]])
+        TS_B3_GSEL(1, s1, s5, s9, s13, m[S.s[r][2]], m[S.s[r][3]])
+        TS_B3_GSEL(2, s2, s6, s10, s14, m[S.s[r][4]], m[S.s[r][5]])
+        TS_B3_GSEL(3, s3, s7, s11, s15, m[S.s[r][6]], m[S.s[r][7]])
+        TS_B3_GSEL(4, s0, s5, s10, s15, m[S.s[r][8]], m[S.s[r][9]])
+        TS_B3_GSEL(5, s1, s6, s11, s12, m[S.s[r][10]], m[S.s[r][11]])
+        TS_B3_GSEL(6, s2, s7, s8, s13, m[S.s[r][12]], m[S.s[r][13]])
+        TS_B3_GSEL(7, s3, s4, s9, s14, m[S.s[r][14]], m[S.s[r][15]])
     }
     cv[0] = s0 ^ s8; cv[1] = s1 ^ s9; cv[2] = s2 ^ s10; cv[3] = s3 ^ s11;
     cv[4] = s4 ^ s12; cv[5] = s5 ^ s13; cv[6] = s6 ^ s14; cv[7] = s7 ^ s15;
@@ -245,7 +278,15 @@ constexpr int FAST_WARPS = 8;
 // [blk_begin, blk_end) is the window of 64-byte blocks absorbed by this launch: the host->device pipeline hashes a
 // row incrementally as its column chunks arrive, the chaining value parked in `digests` between launches (rows of
 // at most one Blake3 chunk, so there is no subtree stack to carry).  A full hash is the window [0, total_blocks).
-__global__ void __launch_bounds__(FAST_WARPS * 32) hash_rows_fast_kernel(FastSegs fs, uint32_t width, size_t n_leaves,
+#ifndef TS_B3_MINBLOCKS
+#define TS_B3_MINBLOCKS 0  // 0 = no register bound: 80 registers, 3 CTAs per SM; bounding it to 64 (4 CTAs) measured slower (10.05 ms)
+#endif
+#if TS_B3_MINBLOCKS > 0
+#define TS_B3_BOUNDS __launch_bounds__(FAST_WARPS * 32, TS_B3_MINBLOCKS)
+#else
+#define TS_B3_BOUNDS __launch_bounds__(FAST_WARPS * 32)
+#endif
+__global__ void TS_B3_BOUNDS hash_rows_fast_kernel(FastSegs fs, uint32_t width, size_t n_leaves,
                                                                         int monty, uint32_t *digests, uint32_t blk_begin,
                                                                         uint32_t blk_end) {
     TS_DYN_SMEM(uint32_t, sm);
